@@ -1,0 +1,152 @@
+/*
+ * sdft_b200.h -- C-ABI of libsdft_b200.so: the B200-native (sm_100a CUDA) replacement for the
+ * analysis/synthesis hot path of jurihock/sdft.
+ *
+ * The library exports one symbol set per (time-domain, frequency-domain) type pair because the
+ * reference selects those types at compile time (c/src/sdft/sdft.h:101-125) and reuses the same
+ * function names for every pair.  Suffix <td><fd> is one of f32f32, f32f64 (the reference default),
+ * f64f32, f64f64; long double has no device equivalent and is rejected by the shim header.
+ * include/c/sdft/sdft.h maps the reference's public names onto these symbols, so existing C callers
+ * only swap the include path and link -lsdft_b200.  include/cpp/sdft/sdft.h does the same for the
+ * C++ template sdft::SDFT<T, F>.
+ *
+ * Pointer arguments (`samples`, `dfts`) may be HOST or DEVICE pointers; the library asks the CUDA
+ * runtime which.  Host pointers: the call copies in/out and returns when the result is in place.
+ * Device pointers: nothing is copied, work is queued on the plan's stream and the call returns at once
+ * (stream-ordered; see sdft_b200_synchronize / sdft_b200_set_stream).
+ *
+ * There is no CPU fallback: if no CUDA device or no sm_100a image is usable, *_alloc* returns NULL and
+ * sdft_b200_last_error_string(NULL) says why.
+ *
+ * Plain C, no CUDA or torch types in any signature.
+ */
+#ifndef SDFT_B200_H
+#define SDFT_B200_H
+
+#include <stddef.h>
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SDFT_B200_API
+#else
+#define SDFT_B200_API __attribute__((visibility("default")))
+#endif
+
+/* interleaved {re, im}; layout-identical to the reference's sdft_fdx_t in all of its three spellings
+ * (C99 complex, _Dcomplex, struct{r,i}: c/src/sdft/sdft.h:84-99), std::complex<F> and numpy complex */
+typedef struct sdft_b200_cf32 { float r, i; } sdft_b200_cf32_t;
+typedef struct sdft_b200_cf64 { double r, i; } sdft_b200_cf64_t;
+
+/* same numbering as enum sdft_window (c/src/sdft/sdft.h:127-133) */
+enum sdft_b200_window
+{
+  sdft_b200_window_boxcar = 0,
+  sdft_b200_window_hann = 1,
+  sdft_b200_window_hamming = 2,
+  sdft_b200_window_blackman = 3
+};
+
+/* opaque device-resident plan (replaces struct sdft_plan, c/src/sdft/sdft.h:175-182) */
+typedef struct sdft_b200_plan sdft_b200_plan_t;
+
+/*
+ * Drop-in entry points, one set per type pair.  Each replaces the reference function named in the
+ * comment; argument meaning and ownership are unchanged (c/src/sdft/sdft.h line in brackets).
+ */
+#define SDFT_B200_DECLARE(SFX, TD, FDX)                                                                        \
+  /* sdft_alloc [457]: hann, latency 1 */                                                                      \
+  SDFT_B200_API sdft_b200_plan_t* sdft_b200_##SFX##_alloc(size_t dftsize);                                     \
+  /* sdft_alloc_custom [413] */                                                                                \
+  SDFT_B200_API sdft_b200_plan_t* sdft_b200_##SFX##_alloc_custom(size_t dftsize, int window, double latency);  \
+  /* extension: `channels` independent plans advanced by one launch (SURVEY 8e channel sharding) */           \
+  SDFT_B200_API sdft_b200_plan_t* sdft_b200_##SFX##_alloc_batch(size_t dftsize, int window, double latency,    \
+                                                                size_t channels);                              \
+  /* sdft_free [466]: NULL is a no-op */                                                                       \
+  SDFT_B200_API void sdft_b200_##SFX##_free(sdft_b200_plan_t* plan);                                           \
+  /* sdft_reset [517] */                                                                                       \
+  SDFT_B200_API void sdft_b200_##SFX##_reset(sdft_b200_plan_t* plan);                                          \
+  /* sdft_size [535], sdft_window [543], sdft_latency [551]: NULL -> 0 / boxcar / 0 */                         \
+  SDFT_B200_API size_t sdft_b200_##SFX##_size(const sdft_b200_plan_t* plan);                                   \
+  SDFT_B200_API int sdft_b200_##SFX##_window(const sdft_b200_plan_t* plan);                                    \
+  SDFT_B200_API double sdft_b200_##SFX##_latency(const sdft_b200_plan_t* plan);                                \
+  /* sdft_sdft [562] */                                                                                        \
+  SDFT_B200_API void sdft_b200_##SFX##_sdft(sdft_b200_plan_t* plan, TD sample, FDX* dft);                      \
+  /* sdft_sdft_n [607]: dfts is (nsamples, dftsize) row-major */                                               \
+  SDFT_B200_API void sdft_b200_##SFX##_sdft_n(sdft_b200_plan_t* plan, size_t nsamples, const TD* samples,      \
+                                              FDX* dfts);                                                      \
+  /* sdft_sdft_nd [622]: dfts is nsamples row pointers */                                                      \
+  SDFT_B200_API void sdft_b200_##SFX##_sdft_nd(sdft_b200_plan_t* plan, size_t nsamples, const TD* samples,     \
+                                               FDX** dfts);                                                    \
+  /* sdft_isdft [635] */                                                                                       \
+  SDFT_B200_API TD sdft_b200_##SFX##_isdft(sdft_b200_plan_t* plan, const FDX* dft);                            \
+  /* sdft_isdft_n [666] */                                                                                     \
+  SDFT_B200_API void sdft_b200_##SFX##_isdft_n(sdft_b200_plan_t* plan, size_t nsamples, const FDX* dfts,       \
+                                               TD* samples);                                                   \
+  /* sdft_isdft_nd [681] */                                                                                    \
+  SDFT_B200_API void sdft_b200_##SFX##_isdft_nd(sdft_b200_plan_t* plan, size_t nsamples, const FDX** dfts,     \
+                                                TD* samples);                                                  \
+  /* extension: analysis state update without writing rows (used to prime a time shard with its         \
+   * 2m-sample halo) */                                                                             \
+  SDFT_B200_API void sdft_b200_##SFX##_advance(sdft_b200_plan_t* plan, size_t nsamples, const TD* samples);    \
+  /* extension, batch plans: samples is (channels, nsamples), dfts is (channels, nsamples, dftsize) */         \
+  SDFT_B200_API void sdft_b200_##SFX##_sdft_batch(sdft_b200_plan_t* plan, size_t nsamples, const TD* samples,  \
+                                                  FDX* dfts);                                                  \
+  SDFT_B200_API void sdft_b200_##SFX##_isdft_batch(sdft_b200_plan_t* plan, size_t nsamples, const FDX* dfts,   \
+                                                   TD* samples);                                               \
+  /* extension: fused analysis -> synthesis round trip (the test/test.c:79-80 pattern) that never       \
+   * materialises the (n, m) matrix; out[t] equals isdft(sdft(in[t])) */                                       \
+  SDFT_B200_API void sdft_b200_##SFX##_roundtrip_n(sdft_b200_plan_t* plan, size_t nsamples, const TD* in,      \
+                                                   TD* out);
+
+SDFT_B200_DECLARE(f32f32, float, sdft_b200_cf32_t)
+SDFT_B200_DECLARE(f32f64, float, sdft_b200_cf64_t)
+SDFT_B200_DECLARE(f64f32, double, sdft_b200_cf32_t)
+SDFT_B200_DECLARE(f64f64, double, sdft_b200_cf64_t)
+
+/*
+ * Type-independent extensions (the plan remembers its type pair).
+ */
+
+/* 0 = ok; otherwise the (sticky) cudaError_t / library error code of the first failure on this plan.
+ * plan == NULL reports the last error of a failed *_alloc* on the calling thread. */
+SDFT_B200_API int sdft_b200_last_error(const sdft_b200_plan_t* plan);
+SDFT_B200_API const char* sdft_b200_last_error_string(const sdft_b200_plan_t* plan);
+
+/* Waits until everything queued on the plan's stream is done.  Returns sdft_b200_last_error. */
+SDFT_B200_API int sdft_b200_synchronize(sdft_b200_plan_t* plan);
+
+/* Makes the plan use a caller-owned stream (a cudaStream_t passed as void*; NULL = legacy default
+ * stream).  The plan's own stream is kept for later sdft_b200_set_stream(plan, (void*)-1). */
+SDFT_B200_API int sdft_b200_set_stream(sdft_b200_plan_t* plan, void* cuda_stream);
+
+/* Scan chunk length in samples (multiple of 32, <= 1024); 0 = choose per call from n and m. */
+SDFT_B200_API int sdft_b200_set_chunk(sdft_b200_plan_t* plan, size_t chunk);
+
+SDFT_B200_API size_t sdft_b200_channels(const sdft_b200_plan_t* plan);
+SDFT_B200_API int sdft_b200_device(const sdft_b200_plan_t* plan);
+/* number of kernels this plan has launched so far (bench.py reports it as gpu_launches) */
+SDFT_B200_API unsigned long long sdft_b200_launch_count(const sdft_b200_plan_t* plan);
+
+/* Introspection used by the parity tests: copies plan tables/state to HOST buffers.
+ * twiddles: analysis and synthesis tables, dftsize complex values each (c/src/sdft/sdft.h:444-445).
+ * state (channel): cursor, history (2*dftsize samples, oldest first), accumulators and current
+ * modulation phase (dftsize complex values each) (c/src/sdft/sdft.h:153-159). */
+SDFT_B200_API int sdft_b200_get_twiddles(sdft_b200_plan_t* plan, void* analysis, void* synthesis);
+SDFT_B200_API int sdft_b200_get_state(sdft_b200_plan_t* plan, size_t channel, size_t* cursor, void* history,
+                                      void* accumulators, void* phase);
+
+/* Page-locked host memory so that host-pointer calls can DMA straight into the caller's buffer. */
+SDFT_B200_API void* sdft_b200_host_alloc(size_t bytes);
+SDFT_B200_API void sdft_b200_host_free(void* ptr);
+
+/* Library build information: "sdft_b200 <version> sm_100a ..." */
+SDFT_B200_API const char* sdft_b200_version(void);
+
+#if defined(__cplusplus)
+}
+#endif
+
+#endif /* SDFT_B200_H */

@@ -1,0 +1,934 @@
+/*
+ * sdft_b200.cu -- host side of libsdft_b200.so: device-resident plan, launch logic and the C-ABI
+ * declared in include/sdft_b200.h.  The kernels are in sdft_kernels.cuh.
+ *
+ * What lives where (reference: struct sdft_plan, c/src/sdft/sdft.h:137-182):
+ *   tables   tw_ext[m+4], tws[m], F0[ceil(2m/32)][m+4]         device, written once per plan
+ *   state    history[2][2m] (ping-pong), acc_state[m+4], phase_state[m+4] per channel; cursor on the host
+ *   scratch  samples, deltas, chunk totals/carries, row tiles   device, grow-only
+ *
+ * No CPU fallback: every entry point either runs the CUDA path or records an error on the plan.
+ */
+#include "../../include/sdft_b200.h"
+#include "sdft_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace sdftb200;
+
+/* ------------------------------------------------------------------------------------------------
+ * plan
+ * ---------------------------------------------------------------------------------------------- */
+enum TypeId { kF32 = 0, kF64 = 1 };
+
+struct Buffer
+{
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+struct sdft_b200_plan
+{
+  int td = kF32, fd = kF64;
+  size_t m = 0;
+  size_t cells = 0;
+  int window = 1;
+  double latency = 1;
+  size_t channels = 1;
+  int device = 0;
+
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t tile_ready[2] = { nullptr, nullptr };
+  cudaEvent_t tile_free[2] = { nullptr, nullptr };
+
+  size_t cursor = 0;
+  size_t forced_chunk = 0;
+  size_t tile_bytes = 0;
+  unsigned long long launches = 0;
+
+  MirrorMap mirrors;
+  void* tw_ext = nullptr;
+  void* tws = nullptr;
+  void* f0 = nullptr;
+  size_t f0_rows = 0;
+
+  void* history[2] = { nullptr, nullptr };
+  int hist_sel = 0;
+  void* acc_state = nullptr;
+  void* phase_state = nullptr;
+
+  Buffer samples, deltas, totals, synth_out, tile[2];
+
+  int status = 0;
+  char errmsg[256] = "";
+};
+
+typedef sdft_b200_plan Plan;
+
+/* ------------------------------------------------------------------------------------------------
+ * errors
+ * ---------------------------------------------------------------------------------------------- */
+namespace
+{
+
+enum { SDFT_B200_ERR_TYPE = 10001, SDFT_B200_ERR_ARG = 10002, SDFT_B200_ERR_NODEVICE = 10003 };
+
+thread_local int g_alloc_error = 0;
+thread_local char g_alloc_errmsg[256] = "";
+
+void plan_fail(Plan* p, int code, const char* what, const char* file, int line);
+
+#define CU_TRY(plan, expr)                                         \
+  do                                                               \
+  {                                                                \
+    cudaError_t e__ = (expr);                                      \
+    if (e__ != cudaSuccess)                                        \
+    {                                                              \
+      plan_fail((plan), (int)e__, #expr, __FILE__, __LINE__);      \
+      return false;                                                \
+    }                                                              \
+  } while (0)
+
+template <typename X> struct type_id;
+template <> struct type_id<float> { static const int value = kF32; };
+template <> struct type_id<double> { static const int value = kF64; };
+
+size_t env_size(const char* name, size_t fallback)
+{
+  const char* v = getenv(name);
+  if (!v || !*v) return fallback;
+  char* end = nullptr;
+  const unsigned long long x = strtoull(v, &end, 10);
+  return (end && end != v) ? (size_t)x : fallback;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * host-side trigonometry with the reference's expression order and types (sdft.h:439-446).
+ * Computed with the host libm so that float tables are bit-identical to the reference's
+ * (SURVEY.md fact 5); the device never evaluates sin/cos.
+ * ---------------------------------------------------------------------------------------------- */
+inline float t_cos(float x) { return ::cosf(x); }
+inline float t_sin(float x) { return ::sinf(x); }
+inline float t_acos(float x) { return ::acosf(x); }
+inline double t_cos(double x) { return ::cos(x); }
+inline double t_sin(double x) { return ::sin(x); }
+inline double t_acos(double x) { return ::acos(x); }
+
+template <typename F>
+void make_tables(size_t m, double latency, std::vector<cx<F>>& tw, std::vector<cx<F>>& tws)
+{
+  tw.resize(m);
+  tws.resize(m);
+  const F omega = (F)(-2) * t_acos((F)(-1)) / (F)(m * 2);
+  const F wsyn = (F)(+2) / ((F)(1) - t_cos((F)((omega * (F)m) * latency)));
+  for (size_t k = 0; k < m; ++k)
+  {
+    const F a = omega * (F)k;
+    tw[k].r = (F)(1) * t_cos(a);
+    tw[k].i = (F)(1) * t_sin(a);
+    const F s = (F)(((omega * (F)k) * (F)m) * latency);   // trailing product in double, then narrowed
+    tws[k].r = wsyn * t_cos(s);
+    tws[k].i = wsyn * t_sin(s);
+  }
+}
+
+/* mirror cells resolved from the assignment order of sdft.h:589-595 */
+MirrorMap make_mirrors(size_t m)
+{
+  MirrorMap mm;
+  mm.cell[0] = 0; mm.cell[1] = 1; mm.cell[2] = (int)m + 2; mm.cell[3] = (int)m + 3;
+  if (m >= 3)
+  {
+    mm.src[0] = 2; mm.conj[0] = 1;
+    mm.src[1] = 1; mm.conj[1] = 1;
+    mm.src[2] = (int)m - 2; mm.conj[2] = 1;
+    mm.src[3] = (int)m - 3; mm.conj[3] = 1;
+  }
+  else if (m == 2)
+  {
+    /* aux[1]=conj(bin1); aux[4]=conj(bin0); aux[0]=conj(aux[4])=bin0; aux[5]=conj(aux[1])=bin1 */
+    mm.src[0] = 0; mm.conj[0] = 0;
+    mm.src[1] = 1; mm.conj[1] = 1;
+    mm.src[2] = 0; mm.conj[2] = 1;
+    mm.src[3] = 1; mm.conj[3] = 0;
+  }
+  else
+  {
+    /* m == 1: each mirror cell only ever copies itself through its partner and stays zero */
+    for (int q = 0; q < 4; ++q) { mm.src[q] = -1; mm.conj[q] = 0; }
+  }
+  return mm;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * plan
+ * ---------------------------------------------------------------------------------------------- */
+void plan_fail(Plan* p, int code, const char* what, const char* file, int line)
+{
+  const char* name = (code < 10000) ? cudaGetErrorString((cudaError_t)code) : "sdft_b200 error";
+  char msg[256];
+  snprintf(msg, sizeof(msg), "%s: %s (%d) at %s:%d", what, name, code, file, line);
+  if (p)
+  {
+    if (p->status == 0)
+    {
+      p->status = code;
+      snprintf(p->errmsg, sizeof(p->errmsg), "%s", msg);
+      fprintf(stderr, "[sdft_b200] %s\n", msg);
+    }
+  }
+  else
+  {
+    g_alloc_error = code;
+    snprintf(g_alloc_errmsg, sizeof(g_alloc_errmsg), "%s", msg);
+    fprintf(stderr, "[sdft_b200] %s\n", msg);
+  }
+  if (code < 10000) cudaGetLastError();
+}
+
+bool reserve(Plan* p, Buffer& b, size_t bytes)
+{
+  if (bytes <= b.bytes) return true;
+  if (b.ptr)
+  {
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    CU_TRY(p, cudaFree(b.ptr));
+    b.ptr = nullptr;
+    b.bytes = 0;
+  }
+  const size_t want = bytes + bytes / 8;
+  CU_TRY(p, cudaMalloc(&b.ptr, want));
+  b.bytes = want;
+  return true;
+}
+
+enum PtrKind { kHostPageable, kHostPinned, kDevice };
+
+PtrKind classify(const void* ptr)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return kHostPageable;
+  }
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return kDevice;
+  if (a.type == cudaMemoryTypeHost) return kHostPinned;
+  return kHostPageable;
+}
+
+template <typename F> size_t csize() { return sizeof(cx<F>); }
+
+/* -------- plan construction -------- */
+template <typename T, typename F>
+bool plan_build(Plan* p)
+{
+  const size_t m = p->m, cells = p->cells, ch = p->channels;
+  std::vector<cx<F>> tw, tws;
+  make_tables<F>(m, p->latency, tw, tws);
+
+  std::vector<cx<F>> tw_ext(cells), p0(cells);
+  for (size_t k = 0; k < m; ++k)
+  {
+    tw_ext[k + 2] = tw[k];
+    p0[k + 2].r = (F)1; p0[k + 2].i = (F)0;
+  }
+  for (int q = 0; q < 4; ++q)
+  {
+    const int c = p->mirrors.cell[q], s = p->mirrors.src[q];
+    if (s < 0)
+    {
+      tw_ext[c].r = tw_ext[c].i = (F)0;
+      p0[c].r = p0[c].i = (F)0;
+    }
+    else
+    {
+      tw_ext[c] = tw[s];
+      if (p->mirrors.conj[q]) tw_ext[c].i = -tw_ext[c].i;
+      p0[c].r = (F)1; p0[c].i = (F)0;
+    }
+  }
+
+  p->f0_rows = (2 * m + kF0Stride - 1) / kF0Stride;
+  CU_TRY(p, cudaMalloc(&p->tw_ext, cells * sizeof(cx<F>)));
+  CU_TRY(p, cudaMalloc(&p->tws, m * sizeof(cx<F>)));
+  CU_TRY(p, cudaMalloc(&p->f0, p->f0_rows * cells * sizeof(cx<F>)));
+  CU_TRY(p, cudaMalloc(&p->history[0], ch * 2 * m * sizeof(T)));
+  CU_TRY(p, cudaMalloc(&p->history[1], ch * 2 * m * sizeof(T)));
+  CU_TRY(p, cudaMalloc(&p->acc_state, ch * cells * sizeof(cx<F>)));
+  CU_TRY(p, cudaMalloc(&p->phase_state, ch * cells * sizeof(cx<F>)));
+
+  CU_TRY(p, cudaMemcpyAsync(p->tw_ext, tw_ext.data(), cells * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
+  CU_TRY(p, cudaMemcpyAsync(p->tws, tws.data(), m * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
+  /* stage P0 in phase_state[channel 0], expand it into the table, then reset copies row 0 everywhere */
+  CU_TRY(p, cudaMemcpyAsync(p->phase_state, p0.data(), cells * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
+  const unsigned threads = 128;
+  phase_table_kernel<F><<<(unsigned)((cells + threads - 1) / threads), threads, 0, p->stream>>>(
+      (const cx<F>*)p->tw_ext, (const cx<F>*)p->phase_state, (cx<F>*)p->f0, (unsigned)cells, (unsigned)(2 * m));
+  p->launches++;
+  CU_TRY(p, cudaGetLastError());
+  CU_TRY(p, cudaStreamSynchronize(p->stream));   // host vectors go out of scope
+  return true;
+}
+
+template <typename T, typename F>
+bool plan_reset(Plan* p)
+{
+  const size_t m = p->m, cells = p->cells, ch = p->channels;
+  p->cursor = 0;
+  p->hist_sel = 0;
+  CU_TRY(p, cudaMemsetAsync(p->history[0], 0, ch * 2 * m * sizeof(T), p->stream));
+  CU_TRY(p, cudaMemsetAsync(p->acc_state, 0, ch * cells * sizeof(cx<F>), p->stream));
+  for (size_t c = 0; c < ch; ++c)
+  {
+    CU_TRY(p, cudaMemcpyAsync((cx<F>*)p->phase_state + c * cells, p->f0, cells * sizeof(cx<F>),
+                              cudaMemcpyDeviceToDevice, p->stream));
+  }
+  return true;
+}
+
+void plan_destroy(Plan* p)
+{
+  if (!p) return;
+  cudaSetDevice(p->device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
+  void* ptrs[] = { p->tw_ext, p->tws, p->f0, p->history[0], p->history[1], p->acc_state, p->phase_state,
+                   p->samples.ptr, p->deltas.ptr, p->totals.ptr, p->synth_out.ptr, p->tile[0].ptr, p->tile[1].ptr };
+  for (void* q : ptrs)
+    if (q) cudaFree(q);
+  for (int i = 0; i < 2; ++i)
+  {
+    if (p->tile_ready[i]) cudaEventDestroy(p->tile_ready[i]);
+    if (p->tile_free[i]) cudaEventDestroy(p->tile_free[i]);
+  }
+  if (p->own_stream) cudaStreamDestroy(p->own_stream);
+  if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+  cudaGetLastError();
+  delete p;
+}
+
+template <typename T, typename F>
+Plan* plan_create(size_t m, int window, double latency, size_t channels)
+{
+  g_alloc_error = 0;
+  g_alloc_errmsg[0] = 0;
+  if (m == 0 || channels == 0 || channels > 65535 || m > (1u << 30) || window < 0 || window > 3)
+  {
+    plan_fail(nullptr, SDFT_B200_ERR_ARG, "sdft_alloc: bad dftsize/window/channels", __FILE__, __LINE__);
+    return nullptr;
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+  {
+    cudaGetLastError();
+    plan_fail(nullptr, SDFT_B200_ERR_NODEVICE, "no CUDA device (libsdft_b200 has no CPU fallback)", __FILE__, __LINE__);
+    return nullptr;
+  }
+  Plan* p = new (std::nothrow) Plan();
+  if (!p) return nullptr;
+  p->td = type_id<T>::value;
+  p->fd = type_id<F>::value;
+  p->m = m;
+  p->cells = m + 4;
+  p->window = window;
+  p->latency = latency;
+  p->channels = channels;
+  p->mirrors = make_mirrors(m);
+  p->tile_bytes = env_size("SDFT_B200_TILE_MB", 128) << 20;
+  p->forced_chunk = env_size("SDFT_B200_CHUNK", 0);
+
+  bool ok = true;
+  const long dev_env = (long)env_size("SDFT_B200_DEVICE", (size_t)-1);
+  cudaError_t e = cudaSuccess;
+  if (dev_env >= 0) e = cudaSetDevice((int)dev_env);
+  if (e == cudaSuccess) e = cudaGetDevice(&p->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i)
+  {
+    e = cudaEventCreateWithFlags(&p->tile_ready[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->tile_free[i], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess)
+  {
+    plan_fail(p, (int)e, "plan_create: stream/event setup", __FILE__, __LINE__);
+    ok = false;
+  }
+  p->stream = p->own_stream;
+  ok = ok && plan_build<T, F>(p) && plan_reset<T, F>(p);
+  if (ok && cudaStreamSynchronize(p->stream) != cudaSuccess) ok = false;
+  if (!ok)
+  {
+    g_alloc_error = p->status ? p->status : (int)cudaGetLastError();
+    snprintf(g_alloc_errmsg, sizeof(g_alloc_errmsg), "%s", p->errmsg);
+    plan_destroy(p);
+    return nullptr;
+  }
+  return p;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * device-side passes
+ * ---------------------------------------------------------------------------------------------- */
+unsigned groups_for(const Plan* p)
+{
+  const unsigned span = (p->window == 0) ? kWarpCells : kWarpCells - 4;
+  return (unsigned)((p->m + span - 1) / span);
+}
+
+unsigned choose_chunk(const Plan* p, size_t n)
+{
+  if (p->forced_chunk)
+  {
+    size_t c = (p->forced_chunk / kF0Stride) * kF0Stride;
+    if (c < (size_t)kF0Stride) c = kF0Stride;
+    if (c > (size_t)kMaxChunk) c = kMaxChunk;
+    return (unsigned)c;
+  }
+  /* enough warps to fill 148 SMs x 16 resident warps a few times over, else the shortest chunk */
+  const double want = 148.0 * 16.0 * 4.0;
+  const double per_sample = (double)groups_for(p) * (double)p->channels;
+  unsigned c = kMaxChunk;
+  while (c > (unsigned)kF0Stride && ((double)n / c) * per_sample < want) c >>= 1;
+  return c;
+}
+
+template <typename F>
+void launch_emit(Plan* p, const EmitArgs<F>& a, dim3 grid, bool vec)
+{
+#define SDFT_EMIT_CASE(W)                                                                              \
+  case W:                                                                                              \
+    if (vec) emit_kernel<F, W, true><<<grid, kEmitWarps * 32, 0, p->stream>>>(a);                      \
+    else emit_kernel<F, W, false><<<grid, kEmitWarps * 32, 0, p->stream>>>(a);                         \
+    break;
+  switch (p->window)
+  {
+    SDFT_EMIT_CASE(0)
+    SDFT_EMIT_CASE(1)
+    SDFT_EMIT_CASE(2)
+    SDFT_EMIT_CASE(3)
+  }
+#undef SDFT_EMIT_CASE
+  p->launches++;
+}
+
+/* analysis over n samples per channel, everything on the device.
+ * x: (channels, x_stride) samples; out: (channels, out_stride) complex rows or nullptr (state only). */
+template <typename T, typename F>
+bool analysis_device(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride)
+{
+  if (n == 0) return true;
+  const unsigned m = (unsigned)p->m;
+  const unsigned ch = (unsigned)p->channels;
+  const unsigned chunk = choose_chunk(p, n);
+  const Schedule sched = make_schedule(p->cursor, n, m, chunk);
+
+  if (!reserve(p, p->deltas, (size_t)ch * n * sizeof(F))) return false;
+  if (!reserve(p, p->totals, (size_t)ch * sched.nchunks * p->cells * sizeof(cx<F>))) return false;
+
+  /* K1 */
+  {
+    const size_t work = n > 2 * (size_t)m ? n : 2 * (size_t)m;
+    unsigned blocks = (unsigned)((work + 255) / 256);
+    if (blocks > 2048) blocks = 2048;
+    delta_kernel<T, F><<<dim3(blocks, ch), 256, 0, p->stream>>>(
+        x, x_stride, (const T*)p->history[p->hist_sel], (T*)p->history[p->hist_sel ^ 1],
+        (F*)p->deltas.ptr, n, n, 2 * m);
+    p->launches++;
+    p->hist_sel ^= 1;
+  }
+
+  ScanArgs<F> s;
+  s.sched = sched;
+  s.delta = (const F*)p->deltas.ptr;
+  s.delta_stride = n;
+  s.tw_ext = (const cx<F>*)p->tw_ext;
+  s.f0 = (const cx<F>*)p->f0;
+  s.phase_state = (cx<F>*)p->phase_state;
+  s.acc_state = (cx<F>*)p->acc_state;
+  s.totals = (cx<F>*)p->totals.ptr;
+  s.m = m;
+  s.cells = (unsigned)p->cells;
+  s.mirrors = p->mirrors;
+
+  /* K2, K2b */
+  {
+    const unsigned bin_blocks = (m + kTotalsThreads - 1) / kTotalsThreads;
+    chunk_totals_kernel<F><<<dim3(sched.nchunks * bin_blocks, ch), kTotalsThreads, 0, p->stream>>>(s);
+    carry_scan_kernel<F><<<dim3(bin_blocks, ch), kTotalsThreads, 0, p->stream>>>(s);
+    p->launches += 2;
+  }
+
+  /* K3 */
+  if (out)
+  {
+    EmitArgs<F> a;
+    a.scan = s;
+    a.out = out;
+    a.out_channel_stride = out_stride;
+    a.groups = groups_for(p);
+    a.group_blocks = (a.groups + kEmitWarps - 1) / kEmitWarps;
+    a.win.w = (F)(1) / (F)(p->m * 2);           // sdft.h:422
+    a.win.wq = a.win.w * (F)(0.25);             // sdft.h:371
+    const size_t pair_bytes = 2 * sizeof(cx<F>);
+    const bool vec = (m % 2 == 0) && (((uintptr_t)out) % pair_bytes == 0) && (out_stride % 2 == 0);
+    launch_emit<F>(p, a, dim3(sched.nchunks * a.group_blocks, ch), vec);
+  }
+  CU_TRY(p, cudaGetLastError());
+  p->cursor = (size_t)((p->cursor + n) % (2 * (size_t)m));
+  return true;
+}
+
+template <typename T, typename F>
+bool synthesis_device(Plan* p, size_t n, const cx<F>* dfts, size_t dft_stride, T* y, size_t y_stride)
+{
+  if (n == 0) return true;
+  const unsigned ch = (unsigned)p->channels;
+  size_t blocks = (n + kSynthWarps - 1) / kSynthWarps;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const dim3 grid((unsigned)blocks, ch);
+  if (p->latency == 1)
+    synth_kernel<T, F, true><<<grid, kSynthWarps * 32, 0, p->stream>>>(dfts, dft_stride, (const cx<F>*)p->tws, y,
+                                                                       y_stride, n, (unsigned)p->m);
+  else
+    synth_kernel<T, F, false><<<grid, kSynthWarps * 32, 0, p->stream>>>(dfts, dft_stride, (const cx<F>*)p->tws, y,
+                                                                        y_stride, n, (unsigned)p->m);
+  p->launches++;
+  CU_TRY(p, cudaGetLastError());
+  return true;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * host/device pointer plumbing
+ * ---------------------------------------------------------------------------------------------- */
+size_t tile_rows(const Plan* p, size_t n, size_t row_bytes)
+{
+  size_t rows = p->tile_bytes / (row_bytes * p->channels);
+  if (rows < 1) rows = 1;
+  if (rows > n) rows = n;
+  return rows;
+}
+
+/* samples -> device (no-op for device pointers).  Layout (channels, n). */
+template <typename T>
+const T* stage_samples(Plan* p, size_t n, const T* samples, bool* ok)
+{
+  *ok = true;
+  if (classify(samples) == kDevice) return samples;
+  const size_t bytes = p->channels * n * sizeof(T);
+  if (!reserve(p, p->samples, bytes)) { *ok = false; return nullptr; }
+  if (cudaMemcpyAsync(p->samples.ptr, samples, bytes, cudaMemcpyHostToDevice, p->stream) != cudaSuccess)
+  {
+    plan_fail(p, (int)cudaGetLastError(), "H2D samples", __FILE__, __LINE__);
+    *ok = false;
+    return nullptr;
+  }
+  return (const T*)p->samples.ptr;
+}
+
+template <typename T, typename F>
+bool do_sdft(Plan* p, size_t n, const T* samples, cx<F>* dfts)
+{
+  if (n == 0) return true;
+  CU_TRY(p, cudaSetDevice(p->device));
+  bool ok = true;
+  const T* x = stage_samples<T>(p, n, samples, &ok);
+  if (!ok) return false;
+  const size_t m = p->m, ch = p->channels;
+
+  if (classify(dfts) == kDevice)
+  {
+    return analysis_device<T, F>(p, n, x, n, dfts, n * m);
+  }
+
+  /* host destination: compute row tiles on the device and stream them out, overlapping the
+   * device-to-host copy of tile i with the kernels of tile i+1 */
+  const size_t row_bytes = m * sizeof(cx<F>);
+  const size_t rows = tile_rows(p, n, row_bytes);
+  const size_t ntiles = (n + rows - 1) / rows;
+  for (int b = 0; b < 2; ++b)
+    if (!reserve(p, p->tile[b], ch * rows * row_bytes)) return false;
+
+  auto compute = [&](size_t i) -> bool
+  {
+    const int b = (int)(i & 1);
+    const size_t t0 = i * rows;
+    const size_t len = (t0 + rows <= n) ? rows : n - t0;
+    if (i >= 2) CU_TRY(p, cudaStreamWaitEvent(p->stream, p->tile_free[b], 0));
+    if (!analysis_device<T, F>(p, len, x + t0, n, (cx<F>*)p->tile[b].ptr, len * m)) return false;
+    CU_TRY(p, cudaEventRecord(p->tile_ready[b], p->stream));
+    return true;
+  };
+  if (!compute(0)) return false;
+  for (size_t i = 0; i < ntiles; ++i)
+  {
+    if (i + 1 < ntiles && !compute(i + 1)) return false;
+    const int b = (int)(i & 1);
+    const size_t t0 = i * rows;
+    const size_t len = (t0 + rows <= n) ? rows : n - t0;
+    CU_TRY(p, cudaStreamWaitEvent(p->copy_stream, p->tile_ready[b], 0));
+    for (size_t c = 0; c < ch; ++c)
+    {
+      CU_TRY(p, cudaMemcpyAsync(dfts + (c * n + t0) * m, (cx<F>*)p->tile[b].ptr + c * len * m, len * row_bytes,
+                                cudaMemcpyDeviceToHost, p->copy_stream));
+    }
+    CU_TRY(p, cudaEventRecord(p->tile_free[b], p->copy_stream));
+  }
+  CU_TRY(p, cudaStreamSynchronize(p->copy_stream));
+  CU_TRY(p, cudaStreamSynchronize(p->stream));
+  return true;
+}
+
+template <typename T, typename F>
+bool do_advance(Plan* p, size_t n, const T* samples)
+{
+  if (n == 0) return true;
+  CU_TRY(p, cudaSetDevice(p->device));
+  bool ok = true;
+  const bool host = classify(samples) != kDevice;
+  const T* x = stage_samples<T>(p, n, samples, &ok);
+  if (!ok) return false;
+  if (!analysis_device<T, F>(p, n, x, n, (cx<F>*)nullptr, 0)) return false;
+  if (host) CU_TRY(p, cudaStreamSynchronize(p->stream));
+  return true;
+}
+
+template <typename T, typename F>
+bool do_isdft(Plan* p, size_t n, const cx<F>* dfts, T* samples)
+{
+  if (n == 0) return true;
+  CU_TRY(p, cudaSetDevice(p->device));
+  const size_t m = p->m, ch = p->channels;
+  const bool out_dev = classify(samples) == kDevice;
+  T* y = samples;
+  if (!out_dev)
+  {
+    if (!reserve(p, p->synth_out, ch * n * sizeof(T))) return false;
+    y = (T*)p->synth_out.ptr;
+  }
+
+  if (classify(dfts) == kDevice)
+  {
+    if (!synthesis_device<T, F>(p, n, dfts, n * m, y, n)) return false;
+  }
+  else
+  {
+    const size_t row_bytes = m * sizeof(cx<F>);
+    const size_t rows = tile_rows(p, n, row_bytes);
+    const size_t ntiles = (n + rows - 1) / rows;
+    for (int b = 0; b < 2; ++b)
+      if (!reserve(p, p->tile[b], ch * rows * row_bytes)) return false;
+    auto upload = [&](size_t i) -> bool
+    {
+      const int b = (int)(i & 1);
+      const size_t t0 = i * rows;
+      const size_t len = (t0 + rows <= n) ? rows : n - t0;
+      if (i >= 2) CU_TRY(p, cudaStreamWaitEvent(p->copy_stream, p->tile_free[b], 0));
+      for (size_t c = 0; c < ch; ++c)
+      {
+        CU_TRY(p, cudaMemcpyAsync((cx<F>*)p->tile[b].ptr + c * len * m, dfts + (c * n + t0) * m, len * row_bytes,
+                                  cudaMemcpyHostToDevice, p->copy_stream));
+      }
+      CU_TRY(p, cudaEventRecord(p->tile_ready[b], p->copy_stream));
+      return true;
+    };
+    /* make sure earlier work on the compute stream that used the tiles is done */
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    if (!upload(0)) return false;
+    for (size_t i = 0; i < ntiles; ++i)
+    {
+      if (i + 1 < ntiles && !upload(i + 1)) return false;
+      const int b = (int)(i & 1);
+      const size_t t0 = i * rows;
+      const size_t len = (t0 + rows <= n) ? rows : n - t0;
+      CU_TRY(p, cudaStreamWaitEvent(p->stream, p->tile_ready[b], 0));
+      if (!synthesis_device<T, F>(p, len, (const cx<F>*)p->tile[b].ptr, len * m, y + t0, n)) return false;
+      CU_TRY(p, cudaEventRecord(p->tile_free[b], p->stream));
+    }
+  }
+  if (!out_dev)
+  {
+    CU_TRY(p, cudaMemcpyAsync(samples, y, ch * n * sizeof(T), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+  }
+  return true;
+}
+
+/* row-pointer variants (sdft.h:622-628, 681-687): rows may be host or device pointers */
+template <typename T, typename F>
+bool do_sdft_nd(Plan* p, size_t n, const T* samples, cx<F>** rows_out)
+{
+  if (n == 0) return true;
+  if (p->channels != 1) { plan_fail(p, SDFT_B200_ERR_ARG, "sdft_nd on a batch plan", __FILE__, __LINE__); return false; }
+  CU_TRY(p, cudaSetDevice(p->device));
+  bool ok = true;
+  const T* x = stage_samples<T>(p, n, samples, &ok);
+  if (!ok) return false;
+  const size_t m = p->m, row_bytes = m * sizeof(cx<F>);
+  const size_t rows = tile_rows(p, n, row_bytes);
+  if (!reserve(p, p->tile[0], rows * row_bytes)) return false;
+  for (size_t t0 = 0; t0 < n; t0 += rows)
+  {
+    const size_t len = (t0 + rows <= n) ? rows : n - t0;
+    if (!analysis_device<T, F>(p, len, x + t0, n, (cx<F>*)p->tile[0].ptr, len * m)) return false;
+    for (size_t i = 0; i < len; ++i)
+    {
+      CU_TRY(p, cudaMemcpyAsync(rows_out[t0 + i], (cx<F>*)p->tile[0].ptr + i * m, row_bytes, cudaMemcpyDefault, p->stream));
+    }
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+  }
+  return true;
+}
+
+template <typename T, typename F>
+bool do_isdft_nd(Plan* p, size_t n, const cx<F>** rows_in, T* samples)
+{
+  if (n == 0) return true;
+  if (p->channels != 1) { plan_fail(p, SDFT_B200_ERR_ARG, "isdft_nd on a batch plan", __FILE__, __LINE__); return false; }
+  CU_TRY(p, cudaSetDevice(p->device));
+  const size_t m = p->m, row_bytes = m * sizeof(cx<F>);
+  const size_t rows = tile_rows(p, n, row_bytes);
+  if (!reserve(p, p->tile[0], rows * row_bytes)) return false;
+  const bool out_dev = classify(samples) == kDevice;
+  T* y = samples;
+  if (!out_dev)
+  {
+    if (!reserve(p, p->synth_out, n * sizeof(T))) return false;
+    y = (T*)p->synth_out.ptr;
+  }
+  for (size_t t0 = 0; t0 < n; t0 += rows)
+  {
+    const size_t len = (t0 + rows <= n) ? rows : n - t0;
+    for (size_t i = 0; i < len; ++i)
+    {
+      CU_TRY(p, cudaMemcpyAsync((cx<F>*)p->tile[0].ptr + i * m, rows_in[t0 + i], row_bytes, cudaMemcpyDefault, p->stream));
+    }
+    if (!synthesis_device<T, F>(p, len, (const cx<F>*)p->tile[0].ptr, len * m, y + t0, n)) return false;
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+  }
+  if (!out_dev)
+  {
+    CU_TRY(p, cudaMemcpyAsync(samples, y, n * sizeof(T), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+  }
+  return true;
+}
+
+/* analysis -> synthesis without handing the matrix to the caller: rows live only in a device tile */
+template <typename T, typename F>
+bool do_roundtrip(Plan* p, size_t n, const T* in, T* out)
+{
+  if (n == 0) return true;
+  CU_TRY(p, cudaSetDevice(p->device));
+  bool ok = true;
+  const T* x = stage_samples<T>(p, n, in, &ok);
+  if (!ok) return false;
+  const size_t m = p->m, ch = p->channels, row_bytes = m * sizeof(cx<F>);
+  const size_t rows = tile_rows(p, n, row_bytes);
+  if (!reserve(p, p->tile[0], ch * rows * row_bytes)) return false;
+  const bool out_dev = classify(out) == kDevice;
+  T* y = out;
+  if (!out_dev)
+  {
+    if (!reserve(p, p->synth_out, ch * n * sizeof(T))) return false;
+    y = (T*)p->synth_out.ptr;
+  }
+  for (size_t t0 = 0; t0 < n; t0 += rows)
+  {
+    const size_t len = (t0 + rows <= n) ? rows : n - t0;
+    if (!analysis_device<T, F>(p, len, x + t0, n, (cx<F>*)p->tile[0].ptr, len * m)) return false;
+    if (!synthesis_device<T, F>(p, len, (const cx<F>*)p->tile[0].ptr, len * m, y + t0, n)) return false;
+  }
+  if (!out_dev)
+  {
+    CU_TRY(p, cudaMemcpyAsync(out, y, ch * n * sizeof(T), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+  }
+  return true;
+}
+
+template <typename T, typename F>
+bool typed(Plan* p, const char* fn)
+{
+  if (!p) return false;
+  if (p->td != type_id<T>::value || p->fd != type_id<F>::value)
+  {
+    plan_fail(p, SDFT_B200_ERR_TYPE, fn, __FILE__, __LINE__);
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+/* ------------------------------------------------------------------------------------------------
+ * C-ABI
+ * ---------------------------------------------------------------------------------------------- */
+#define SDFT_B200_DEFINE(SFX, TD, FD, FDX)                                                                      \
+  extern "C" sdft_b200_plan_t* sdft_b200_##SFX##_alloc_batch(size_t m, int window, double latency, size_t ch)  \
+  {                                                                                                             \
+    return plan_create<TD, FD>(m, window, latency, ch);                         \
+  }                                                                                                             \
+  extern "C" sdft_b200_plan_t* sdft_b200_##SFX##_alloc_custom(size_t m, int window, double latency)            \
+  {                                                                                                             \
+    return sdft_b200_##SFX##_alloc_batch(m, window, latency, 1);                                                \
+  }                                                                                                             \
+  extern "C" sdft_b200_plan_t* sdft_b200_##SFX##_alloc(size_t m)                                                \
+  {                                                                                                             \
+    return sdft_b200_##SFX##_alloc_batch(m, sdft_b200_window_hann, 1.0, 1);                                     \
+  }                                                                                                             \
+  extern "C" void sdft_b200_##SFX##_free(sdft_b200_plan_t* p) { plan_destroy(p); }                              \
+  extern "C" void sdft_b200_##SFX##_reset(sdft_b200_plan_t* p)                                                  \
+  {                                                                                                             \
+    if (typed<TD, FD>(p, "sdft_reset: plan type mismatch")) plan_reset<TD, FD>(p);                              \
+  }                                                                                                             \
+  extern "C" size_t sdft_b200_##SFX##_size(const sdft_b200_plan_t* p) { return p ? p->m : 0; }                  \
+  extern "C" int sdft_b200_##SFX##_window(const sdft_b200_plan_t* p) { return p ? p->window : 0; }              \
+  extern "C" double sdft_b200_##SFX##_latency(const sdft_b200_plan_t* p) { return p ? p->latency : 0; }         \
+  extern "C" void sdft_b200_##SFX##_sdft_n(sdft_b200_plan_t* p, size_t n, const TD* x, FDX* d)                  \
+  {                                                                                                             \
+    if (typed<TD, FD>(p, "sdft_sdft_n: plan type mismatch")) do_sdft<TD, FD>(p, n, x, (cx<FD>*)d);              \
+  }                                                                                                             \
+  extern "C" void sdft_b200_##SFX##_sdft_batch(sdft_b200_plan_t* p, size_t n, const TD* x, FDX* d)              \
+  {                                                                                                             \
+    if (typed<TD, FD>(p, "sdft_sdft_batch: plan type mismatch")) do_sdft<TD, FD>(p, n, x, (cx<FD>*)d);          \
+  }                                                                                                             \
+  extern "C" void sdft_b200_##SFX##_sdft(sdft_b200_plan_t* p, TD sample, FDX* d)                                \
+  {                                                                                                             \
+    if (typed<TD, FD>(p, "sdft_sdft: plan type mismatch")) do_sdft<TD, FD>(p, 1, &sample, (cx<FD>*)d);          \
+  }                                                                                                             \
+  extern "C" void sdft_b200_##SFX##_sdft_nd(sdft_b200_plan_t* p, size_t n, const TD* x, FDX** d)                \
+  {                                                                                                             \
+    if (typed<TD, FD>(p, "sdft_sdft_nd: plan type mismatch")) do_sdft_nd<TD, FD>(p, n, x, (cx<FD>**)d);         \
+  }                                                                                                             \
+  extern "C" void sdft_b200_##SFX##_advance(sdft_b200_plan_t* p, size_t n, const TD* x)                         \
+  {                                                                                                             \
+    if (typed<TD, FD>(p, "sdft_advance: plan type mismatch")) do_advance<TD, FD>(p, n, x);                      \
+  }                                                                                                             \
+  extern "C" void sdft_b200_##SFX##_isdft_n(sdft_b200_plan_t* p, size_t n, const FDX* d, TD* y)                 \
+  {                                                                                                             \
+    if (typed<TD, FD>(p, "sdft_isdft_n: plan type mismatch")) do_isdft<TD, FD>(p, n, (const cx<FD>*)d, y);      \
+  }                                                                                                             \
+  extern "C" void sdft_b200_##SFX##_isdft_batch(sdft_b200_plan_t* p, size_t n, const FDX* d, TD* y)             \
+  {                                                                                                             \
+    if (typed<TD, FD>(p, "sdft_isdft_batch: plan type mismatch")) do_isdft<TD, FD>(p, n, (const cx<FD>*)d, y);  \
+  }                                                                                                             \
+  extern "C" TD sdft_b200_##SFX##_isdft(sdft_b200_plan_t* p, const FDX* d)                                      \
+  {                                                                                                             \
+    TD y = 0;                                                                                                   \
+    if (typed<TD, FD>(p, "sdft_isdft: plan type mismatch")) do_isdft<TD, FD>(p, 1, (const cx<FD>*)d, &y);       \
+    return y;                                                                                                   \
+  }                                                                                                             \
+  extern "C" void sdft_b200_##SFX##_isdft_nd(sdft_b200_plan_t* p, size_t n, const FDX** d, TD* y)               \
+  {                                                                                                             \
+    if (typed<TD, FD>(p, "sdft_isdft_nd: plan type mismatch")) do_isdft_nd<TD, FD>(p, n, (const cx<FD>**)d, y); \
+  }                                                                                                             \
+  extern "C" void sdft_b200_##SFX##_roundtrip_n(sdft_b200_plan_t* p, size_t n, const TD* in, TD* out)           \
+  {                                                                                                             \
+    if (typed<TD, FD>(p, "sdft_roundtrip_n: plan type mismatch")) do_roundtrip<TD, FD>(p, n, in, out);          \
+  }
+
+SDFT_B200_DEFINE(f32f32, float, float, sdft_b200_cf32_t)
+SDFT_B200_DEFINE(f32f64, float, double, sdft_b200_cf64_t)
+SDFT_B200_DEFINE(f64f32, double, float, sdft_b200_cf32_t)
+SDFT_B200_DEFINE(f64f64, double, double, sdft_b200_cf64_t)
+
+extern "C" int sdft_b200_last_error(const sdft_b200_plan_t* p) { return p ? p->status : g_alloc_error; }
+
+extern "C" const char* sdft_b200_last_error_string(const sdft_b200_plan_t* p)
+{
+  return p ? p->errmsg : g_alloc_errmsg;
+}
+
+extern "C" int sdft_b200_synchronize(sdft_b200_plan_t* p)
+{
+  if (!p) return SDFT_B200_ERR_ARG;
+  cudaSetDevice(p->device);
+  cudaError_t e = cudaStreamSynchronize(p->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(p->copy_stream);
+  if (e != cudaSuccess) plan_fail(p, (int)e, "sdft_b200_synchronize", __FILE__, __LINE__);
+  return p->status;
+}
+
+extern "C" int sdft_b200_set_stream(sdft_b200_plan_t* p, void* cuda_stream)
+{
+  if (!p) return SDFT_B200_ERR_ARG;
+  cudaSetDevice(p->device);
+  cudaStreamSynchronize(p->stream);
+  p->stream = (cuda_stream == (void*)-1) ? p->own_stream : (cudaStream_t)cuda_stream;
+  return p->status;
+}
+
+extern "C" int sdft_b200_set_chunk(sdft_b200_plan_t* p, size_t chunk)
+{
+  if (!p) return SDFT_B200_ERR_ARG;
+  p->forced_chunk = chunk;
+  return 0;
+}
+
+extern "C" size_t sdft_b200_channels(const sdft_b200_plan_t* p) { return p ? p->channels : 0; }
+extern "C" int sdft_b200_device(const sdft_b200_plan_t* p) { return p ? p->device : -1; }
+extern "C" unsigned long long sdft_b200_launch_count(const sdft_b200_plan_t* p) { return p ? p->launches : 0; }
+
+extern "C" int sdft_b200_get_twiddles(sdft_b200_plan_t* p, void* analysis, void* synthesis)
+{
+  if (!p) return SDFT_B200_ERR_ARG;
+  cudaSetDevice(p->device);
+  const size_t cbytes = (p->fd == kF32) ? sizeof(cx<float>) : sizeof(cx<double>);
+  cudaError_t e = cudaStreamSynchronize(p->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(analysis, (char*)p->tw_ext + 2 * cbytes, p->m * cbytes, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(synthesis, p->tws, p->m * cbytes, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) plan_fail(p, (int)e, "sdft_b200_get_twiddles", __FILE__, __LINE__);
+  return p->status;
+}
+
+extern "C" int sdft_b200_get_state(sdft_b200_plan_t* p, size_t channel, size_t* cursor, void* history,
+                                   void* accumulators, void* phase)
+{
+  if (!p || channel >= p->channels) return SDFT_B200_ERR_ARG;
+  cudaSetDevice(p->device);
+  const size_t cbytes = (p->fd == kF32) ? sizeof(cx<float>) : sizeof(cx<double>);
+  const size_t tbytes = (p->td == kF32) ? sizeof(float) : sizeof(double);
+  cudaError_t e = cudaStreamSynchronize(p->stream);
+  if (cursor) *cursor = p->cursor;
+  if (e == cudaSuccess && history)
+    e = cudaMemcpy(history, (char*)p->history[p->hist_sel] + channel * 2 * p->m * tbytes, 2 * p->m * tbytes,
+                   cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && accumulators)
+    e = cudaMemcpy(accumulators, (char*)p->acc_state + (channel * p->cells + 2) * cbytes, p->m * cbytes,
+                   cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && phase)
+    e = cudaMemcpy(phase, (char*)p->phase_state + (channel * p->cells + 2) * cbytes, p->m * cbytes,
+                   cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) plan_fail(p, (int)e, "sdft_b200_get_state", __FILE__, __LINE__);
+  return p->status;
+}
+
+extern "C" void* sdft_b200_host_alloc(size_t bytes)
+{
+  void* ptr = nullptr;
+  if (cudaMallocHost(&ptr, bytes) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return ptr;
+}
+
+extern "C" void sdft_b200_host_free(void* ptr)
+{
+  if (ptr) cudaFreeHost(ptr);
+}
+
+extern "C" const char* sdft_b200_version(void)
+{
+  return "sdft_b200 0.1 (sm_100a; analysis: chunked two-pass scan; synthesis: warp reduction)";
+}

@@ -1,0 +1,188 @@
+"""
+Python ``SDFT`` class over the C-ABI CUDA library.
+
+Mirrors the reference's NumPy class (python/src/sdft/sdft.py:25-203): same constructor arguments, same
+``size`` / ``window`` / ``latency`` attributes, ``reset()``, ``sdft(samples) -> (samples, bins)`` and
+``isdft(dfts) -> (samples,)``.  The arithmetic is NOT done here: every call goes through
+``libsdft_b200.so`` (include/sdft_b200.h) and runs on the GPU.  There is no CPU fallback.
+
+Differences from the reference class, all additive:
+  * ``td`` / ``fd`` select the time/frequency-domain precision ("f32" or "f64"); the default
+    (f64, f64) is what the reference's float64/complex128 NumPy code computes in.
+  * CUDA tensors (torch) are accepted and returned without leaving the device.
+  * the plan follows the C implementation exactly, including the periodic modulation restart that
+    makes it endlessly stable (c/src/sdft/sdft.h:566-576); the reference Python class lets its phase
+    offset grow without bound (sdft.py:101).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+WINDOWS = ("boxcar", "hann", "hamming", "blackman")
+_NP_TD = {"f32": np.float32, "f64": np.float64}
+_NP_FD = {"f32": np.complex64, "f64": np.complex128}
+
+
+def _window_id(window):
+    if isinstance(window, str):
+        w = window.lower()
+        # the reference matches by substring (sdft.py:160-186) and falls back to boxcar
+        for i in (1, 2, 3):
+            if w and w in WINDOWS[i]:
+                return i
+        return 0
+    return int(window)
+
+
+def _is_torch_cuda(x):
+    return type(x).__module__.startswith("torch") and hasattr(x, "is_cuda") and x.is_cuda
+
+
+class SDFT:
+    """Sliding Discrete Fourier Transform (SDFT) on a B200."""
+
+    def __init__(self, dftsize, window="hann", latency=1, td="f64", fd="f64", channels=1):
+        self.size = int(dftsize)
+        self.window = window
+        self.latency = latency
+        self.td, self.fd = td, fd
+        self.channels = int(channels)
+        self._sfx = td + fd
+        self._lib = _lib.load()
+        self._f = lambda name: _lib.fn(self._lib, self._sfx, name)
+        self._h = self._f("alloc_batch")(self.size, _window_id(window), float(latency), self.channels)
+        if not self._h:
+            msg = self._lib.sdft_b200_last_error_string(None)
+            raise RuntimeError("sdft_b200: plan allocation failed: %s" % (msg.decode() if msg else "?"))
+        self._h = ctypes.c_void_p(self._h)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._f("free")(h)
+            except Exception:
+                pass
+
+    # ---- helpers -------------------------------------------------------------------------------
+    def _check(self):
+        code = self._lib.sdft_b200_last_error(self._h)
+        if code:
+            raise RuntimeError("sdft_b200: %s" % self._lib.sdft_b200_last_error_string(self._h).decode())
+
+    def _use_torch_stream(self):
+        import torch
+        self._lib.sdft_b200_set_stream(self._h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+
+    def synchronize(self):
+        self._lib.sdft_b200_synchronize(self._h)
+        self._check()
+
+    @property
+    def launches(self):
+        return int(self._lib.sdft_b200_launch_count(self._h))
+
+    # ---- reference API ---------------------------------------------------------------------------
+    def reset(self):
+        """Reset this SDFT plan to its initial state (sdft.py:67-74)."""
+        self._f("reset")(self._h)
+        self._check()
+
+    def sdft(self, samples):
+        """Estimate the DFT matrix for the given sample array (sdft.py:76-120).
+
+        Returns (samples, bins); for a batch plan the input is (channels, samples) and the result
+        (channels, samples, bins)."""
+        if _is_torch_cuda(samples):
+            import torch
+            x = samples.to(torch.float32 if self.td == "f32" else torch.float64).contiguous()
+            n = x.shape[-1]
+            shape = (n, self.size) if self.channels == 1 else (self.channels, n, self.size)
+            out = torch.empty(shape, dtype=torch.complex64 if self.fd == "f32" else torch.complex128, device=x.device)
+            self._use_torch_stream()
+            self._f("sdft_batch")(self._h, n, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()))
+            self._check()
+            return out
+        x = np.ascontiguousarray(np.atleast_1d(samples), dtype=_NP_TD[self.td])
+        if self.channels == 1:
+            assert x.ndim == 1, f'Expected 1D array (samples,), got {x.shape}!'
+        else:
+            assert x.ndim == 2 and x.shape[0] == self.channels, f'Expected (channels,samples), got {x.shape}!'
+        n = x.shape[-1]
+        shape = (n, self.size) if self.channels == 1 else (self.channels, n, self.size)
+        out = np.empty(shape, _NP_FD[self.fd])
+        self._f("sdft_batch")(self._h, n, x.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p))
+        self._check()
+        return out
+
+    def isdft(self, dfts):
+        """Synthesize the sample array from the given DFT matrix (sdft.py:122-145)."""
+        if _is_torch_cuda(dfts):
+            import torch
+            d = dfts.to(torch.complex64 if self.fd == "f32" else torch.complex128).contiguous()
+            n = d.shape[-2]
+            shape = (n,) if self.channels == 1 else (self.channels, n)
+            y = torch.empty(shape, dtype=torch.float32 if self.td == "f32" else torch.float64, device=d.device)
+            self._use_torch_stream()
+            self._f("isdft_batch")(self._h, n, ctypes.c_void_p(d.data_ptr()), ctypes.c_void_p(y.data_ptr()))
+            self._check()
+            return y
+        d = np.ascontiguousarray(np.atleast_2d(dfts), dtype=_NP_FD[self.fd])
+        assert d.shape[-1] == self.size, f'Expected (samples,frequencies), got {d.shape}!'
+        n = d.shape[-2]
+        shape = (n,) if self.channels == 1 else (self.channels, n)
+        y = np.empty(shape, _NP_TD[self.td])
+        self._f("isdft_batch")(self._h, n, d.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p))
+        self._check()
+        return y
+
+    # ---- extensions ------------------------------------------------------------------------------
+    def advance(self, samples):
+        """Update the analysis state with ``samples`` without producing rows (time-shard priming)."""
+        if _is_torch_cuda(samples):
+            import torch
+            x = samples.to(torch.float32 if self.td == "f32" else torch.float64).contiguous()
+            self._use_torch_stream()
+            self._f("advance")(self._h, x.shape[-1], ctypes.c_void_p(x.data_ptr()))
+        else:
+            x = np.ascontiguousarray(np.atleast_1d(samples), dtype=_NP_TD[self.td])
+            self._f("advance")(self._h, x.shape[-1], x.ctypes.data_as(ctypes.c_void_p))
+        self._check()
+
+    def roundtrip(self, samples):
+        """isdft(sdft(samples)) without materialising the DFT matrix for the caller."""
+        if _is_torch_cuda(samples):
+            import torch
+            x = samples.to(torch.float32 if self.td == "f32" else torch.float64).contiguous()
+            y = torch.empty_like(x)
+            self._use_torch_stream()
+            self._f("roundtrip_n")(self._h, x.shape[-1], ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()))
+            self._check()
+            return y
+        x = np.ascontiguousarray(np.atleast_1d(samples), dtype=_NP_TD[self.td])
+        y = np.empty_like(x)
+        self._f("roundtrip_n")(self._h, x.shape[-1], x.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p))
+        self._check()
+        return y
+
+    def twiddles(self):
+        a = np.empty(self.size, _NP_FD[self.fd])
+        s = np.empty(self.size, _NP_FD[self.fd])
+        self._lib.sdft_b200_get_twiddles(self._h, a.ctypes.data_as(ctypes.c_void_p), s.ctypes.data_as(ctypes.c_void_p))
+        self._check()
+        return a, s
+
+    def state(self, channel=0):
+        cur = ctypes.c_size_t(0)
+        hist = np.empty(2 * self.size, _NP_TD[self.td])
+        acc = np.empty(self.size, _NP_FD[self.fd])
+        ph = np.empty(self.size, _NP_FD[self.fd])
+        self._lib.sdft_b200_get_state(self._h, channel, ctypes.byref(cur), hist.ctypes.data_as(ctypes.c_void_p),
+                                      acc.ctypes.data_as(ctypes.c_void_p), ph.ctypes.data_as(ctypes.c_void_p))
+        self._check()
+        return int(cur.value), hist, acc, ph
+
+    def set_chunk(self, chunk):
+        self._lib.sdft_b200_set_chunk(self._h, int(chunk))

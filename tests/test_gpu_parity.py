@@ -1,0 +1,241 @@
+"""
+Parity of the CUDA path (through the C-ABI library) against the CPU oracle on identical inputs.
+Tolerances are BASELINE.json's: max |X_gpu - X_ref| / max |X_ref| <= 1e-9 for double frequency-domain
+data and <= 1e-4 for float; synthesized samples agree to float rounding.
+"""
+import ctypes
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f64": 1e-9, "f32": 1e-4}
+TYPES = list(itertools.product(["f32", "f64"], repeat=2))
+
+
+@pytest.fixture(scope="module")
+def SDFT():
+    import torch
+    assert torch.cuda.is_available()
+    from sdft_b200 import SDFT
+    return SDFT
+
+
+def rel_err(got, want):
+    scale = np.abs(want).max()
+    return np.abs(got - want).max() / (scale if scale > 0 else 1.0)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint8)
+
+
+@pytest.mark.parametrize("fd", ["f32", "f64"])
+@pytest.mark.parametrize("m", [1, 2, 3, 8, 37, 1000, 1024, 4096])
+def test_tables_bit_identical(SDFT, fd, m):
+    """Twiddle tables come from the host libm with the reference's expression order (sdft.h:439-446)."""
+    from oracle import Oracle
+    for latency in (1.0, 0.5, 0.3):
+        g = SDFT(m, "hann", latency, td="f32", fd=fd)
+        o = Oracle("f32", fd, m, "hann", latency)
+        for a, b in zip(g.twiddles(), o.twiddles()):
+            assert np.array_equal(_bits(a), _bits(b))
+
+
+@pytest.mark.parametrize("td,fd", TYPES)
+@pytest.mark.parametrize("window", ["boxcar", "hann", "hamming", "blackman"])
+@pytest.mark.parametrize("latency", [1.0, 0.5])
+def test_multicall_stream(SDFT, td, fd, window, latency):
+    """Endless multi-call state: odd call sizes crossing the ring wrap and the modulation restart."""
+    from oracle import Oracle
+    rng = np.random.default_rng(abs(hash((td, fd, window))) % 65536)
+    for m in (1, 2, 3, 8, 37, 250, 1000):
+        g = SDFT(m, window, latency, td=td, fd=fd)
+        o = Oracle(td, fd, m, window, latency)
+        for n in (1, 7, 100, 2 * m + 13, 5, 4 * m, 333):
+            x = rng.uniform(-1, 1, n)
+            want = o.sdft(x)
+            got = g.sdft(x)
+            assert got.shape == want.shape and got.dtype == want.dtype
+            assert rel_err(got, want) <= TOL[fd], (m, n, rel_err(got, want))
+            ys, yw = g.isdft(got), o.isdft(want)
+            assert np.abs(ys.astype(np.float64) - yw.astype(np.float64)).max() <= (2e-6 if fd == "f64" else 2e-4), (m, n)
+        cg, hg, ag, pg = g.state()
+        co, ho, ao, po = o.state()
+        assert cg == co
+        assert np.array_equal(_bits(hg), _bits(ho))
+        assert rel_err(ag, ao) <= TOL[fd]
+        if fd == "f32":
+            assert np.array_equal(_bits(pg), _bits(po)), "float modulation phase must be bit-exact"
+        else:
+            assert np.abs(pg - po).max() <= 1e-12
+
+
+@pytest.mark.parametrize("fd", ["f32", "f64"])
+@pytest.mark.parametrize("chunk", [32, 64, 96, 256, 1024])
+def test_chunk_lengths(SDFT, fd, chunk):
+    """Any chunk length (multiple of 32) gives the same rows; resets fall inside and between chunks."""
+    from oracle import Oracle
+    rng = np.random.default_rng(chunk)
+    for m in (37, 1000, 1024):
+        g = SDFT(m, "blackman", 0.5, td="f32", fd=fd)
+        g.set_chunk(chunk)
+        o = Oracle("f32", fd, m, "blackman", 0.5)
+        for n in (777, 2 * m + 13, 3000):
+            x = rng.uniform(-1, 1, n).astype(np.float32)
+            want, got = o.sdft(x), g.sdft(x)
+            assert rel_err(got, want) <= TOL[fd], (m, n, rel_err(got, want))
+
+
+def test_float_rows_close_to_bit_exact(SDFT):
+    """With one chunk per call the float path follows the reference's summation order exactly."""
+    from oracle import Oracle
+    m = 64
+    g = SDFT(m, "hann", 1, td="f32", fd="f32")
+    g.set_chunk(1024)
+    o = Oracle("f32", "f32", m, "hann", 1.0)
+    x = np.random.default_rng(5).uniform(-1, 1, 2 * m).astype(np.float32)
+    want, got = o.sdft(x), g.sdft(x)
+    assert np.array_equal(_bits(got), _bits(want))
+
+
+def test_reset_and_getters(SDFT):
+    from oracle import Oracle
+    g = SDFT(16, "hamming", 0.5, td="f32", fd="f64")
+    x = np.linspace(-1, 1, 77).astype(np.float32)
+    first = g.sdft(x)
+    g.reset()
+    again = g.sdft(x)
+    assert np.array_equal(_bits(first), _bits(again))
+    lib = g._lib
+    assert lib.sdft_b200_f32f64_size(g._h) == 16
+    assert lib.sdft_b200_f32f64_window(g._h) == 2
+    assert lib.sdft_b200_f32f64_latency(g._h) == 0.5
+    # NULL handling of sdft.h:468, 537, 545, 553
+    assert lib.sdft_b200_f32f64_size(None) == 0
+    assert lib.sdft_b200_f32f64_window(None) == 0
+    assert lib.sdft_b200_f32f64_latency(None) == 0.0
+    lib.sdft_b200_f32f64_free(None)
+    # default plan = hann, latency 1 (sdft.h:457-460)
+    h = ctypes.c_void_p(lib.sdft_b200_f32f64_alloc(8))
+    assert lib.sdft_b200_f32f64_window(h) == 1 and lib.sdft_b200_f32f64_latency(h) == 1.0
+    lib.sdft_b200_f32f64_free(h)
+
+
+def test_single_sample_and_row_pointer_variants(SDFT):
+    """sdft_sdft / sdft_isdft (sdft.h:562, 635) and the _nd variants (sdft.h:622, 681)."""
+    from oracle import Oracle
+    m, n = 24, 50
+    g = SDFT(m, "hann", 1, td="f32", fd="f64")
+    o = Oracle("f32", "f64", m, "hann", 1.0)
+    lib = g._lib
+    x = np.random.default_rng(11).uniform(-1, 1, n).astype(np.float32)
+    want = o.sdft(x)
+    row = np.empty(m, np.complex128)
+    for t in range(10):
+        lib.sdft_b200_f32f64_sdft(g._h, ctypes.c_float(x[t]), row.ctypes.data_as(ctypes.c_void_p))
+        assert rel_err(row, want[t]) <= 1e-9
+        y = lib.sdft_b200_f32f64_isdft(g._h, row.ctypes.data_as(ctypes.c_void_p))
+        assert abs(y - o.isdft(want[t:t + 1])[0]) <= 2e-6
+    rows = [np.empty(m, np.complex128) for _ in range(n - 10)]
+    ptrs = (ctypes.c_void_p * len(rows))(*[r.ctypes.data for r in rows])
+    xs = np.ascontiguousarray(x[10:])
+    lib.sdft_b200_f32f64_sdft_nd(g._h, len(rows), xs.ctypes.data_as(ctypes.c_void_p), ptrs)
+    got = np.stack(rows)
+    assert rel_err(got, want[10:]) <= 1e-9
+    y = np.empty(len(rows), np.float32)
+    lib.sdft_b200_f32f64_isdft_nd(g._h, len(rows), ptrs, y.ctypes.data_as(ctypes.c_void_p))
+    assert np.abs(y - o.isdft(want[10:])).max() <= 2e-6
+
+
+def test_device_pointers_and_batch(SDFT):
+    """Device-resident path (torch tensors) and the batched multi-channel plan."""
+    import torch
+    from oracle import Oracle
+    m, n, ch = 250, 3000, 3
+    rng = np.random.default_rng(21)
+    x = rng.uniform(-1, 1, (ch, n)).astype(np.float32)
+    g = SDFT(m, "hann", 0.5, td="f32", fd="f64", channels=ch)
+    xt = torch.from_numpy(x).cuda()
+    parts, ys = [], []
+    for a, b in ((0, 1000), (1000, 1001), (1001, 3000)):
+        d = g.sdft(xt[:, a:b].contiguous())
+        parts.append(d)
+        ys.append(g.isdft(d))
+    torch.cuda.synchronize()
+    got = torch.cat(parts, dim=1).cpu().numpy()
+    y = torch.cat(ys, dim=1).cpu().numpy()
+    for c in range(ch):
+        o = Oracle("f32", "f64", m, "hann", 0.5)
+        want = o.sdft(x[c])
+        assert rel_err(got[c], want) <= 1e-9, c
+        assert np.abs(y[c] - o.isdft(want)).max() <= 2e-6
+    # host batch path
+    g2 = SDFT(m, "hann", 0.5, td="f32", fd="f64", channels=ch)
+    got2 = g2.sdft(x)
+    assert np.array_equal(_bits(got2), _bits(got))
+
+
+def test_advance_and_roundtrip(SDFT):
+    from oracle import Oracle
+    m = 128
+    rng = np.random.default_rng(31)
+    x = rng.uniform(-1, 1, 4 * m + 100).astype(np.float32)
+    o = Oracle("f32", "f64", m, "hann", 1.0)
+    want = o.sdft(x)
+    g = SDFT(m, "hann", 1, td="f32", fd="f64")
+    g.advance(x[:2 * m + 7])
+    got = g.sdft(x[2 * m + 7:])
+    assert rel_err(got, want[2 * m + 7:]) <= 1e-9
+    g.reset()
+    y = g.roundtrip(x)
+    assert np.abs(y - o.isdft(want)).max() <= 2e-6
+
+
+def test_host_tiling_matches_single_pass(SDFT, monkeypatch):
+    """Host destinations are produced in device tiles; tiny tiles must not change a bit."""
+    m, n = 64, 5000
+    x = np.random.default_rng(41).uniform(-1, 1, n).astype(np.float32)
+    g = SDFT(m, "hann", 1, td="f32", fd="f64")
+    g.set_chunk(64)
+    full = g.sdft(x)
+    monkeypatch.setenv("SDFT_B200_TILE_MB", "1")
+    g2 = SDFT(m, "hann", 1, td="f32", fd="f64")
+    g2.set_chunk(64)
+    tiled = g2.sdft(x)
+    assert rel_err(tiled, full) <= 1e-13
+    y1, y2 = g.isdft(full), g2.isdft(full)
+    assert np.array_equal(y1, y2)
+
+
+def test_config1_testwav(SDFT, golden_dir):
+    """BASELINE config 1: test/test.wav, m=1024, hann, f32 TD / f64 FD, latency 1; whole signal in
+    4096-sample calls, against the oracle, the golden rows and the reference's reconstruction SNR."""
+    from oracle import Oracle
+    g = np.load(os.path.join(golden_dir, "testwav.npz"))
+    x = (g["pcm24"].astype(np.float64) / 8388608.0).astype(np.float32)
+    n, call, m = int(g["c1_n"]), 4096, 1024
+    gpu = SDFT(m, "hann", 1, td="f32", fd="f64")
+    cpu = Oracle("f32", "f64", m, "hann", 1.0)
+    want_t = list(g["c1_row_t"])
+    ys, k, worst = [], 0, 0.0
+    for c in range(n // call):
+        seg = x[c * call:(c + 1) * call]
+        got = gpu.sdft(seg)
+        want = cpu.sdft(seg)
+        worst = max(worst, rel_err(got, want))
+        ys.append(gpu.isdft(got))
+        if k < len(want_t) and want_t[k] == c * call + call - 1:
+            assert rel_err(got[-1], g["c1_rows"][k]) <= 1e-9
+            k += 1
+    assert worst <= 1e-9, worst
+    y = np.concatenate(ys)
+    assert np.abs(y[::int(g["c1_y_stride"])] - g["c1_y_strided"]).max() <= 2e-6
+    delay = m - 1
+    xd = x[:n - delay].astype(np.float64)
+    e = y[delay:].astype(np.float64) - xd
+    snr = 10 * np.log10(np.mean(xd ** 2) / np.mean(e ** 2))
+    assert abs(snr - float(g["c1_snr_db"])) < 0.01
