@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the sliding-DFT hot path (BASELINE.json: "analysis bin-updates/s +
+synth samples/s at 1/2/4/8 B200, % HBM roofline").
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): 2^20 samples of white noise, m = 4096 bins, float time domain /
+double frequency domain, all four windows.  One STEP = the analysis (sdft_sdft_n) of the whole signal
+once per window, i.e. 4 * 2^20 * 4096 bin-updates, with samples and the (n, m) output resident in HBM
+(64 GiB written per window, so nothing is absorbed by the 126 MB L2 and no flush is needed).
+At N > 1 every rank runs that same workload on its own channel (channel sharding, no data-path
+collective): weak scaling, `value` = bin-updates of all ranks / max-over-ranks device time.
+
+Extra keys on the JSON line:
+  synthesis     sdft_isdft_n over the same matrix: samples/s and its own read roofline
+  e2e           the same analysis metric through the C-ABI with HOST buffers (pinned), host->device and
+                device->host copies inside the timed region (bounded sample, see e2e.sample)
+  roofline      dominant kernel (analysis emit): algorithmic bytes / CUDA-event launch duration vs the
+                measured HBM peak in MEASURED_PEAKS.json
+  cpu_baseline  the reference's own C path (oracle/_ref, else the oracle port) on the box's host cores
+                (rank 0, N = 1 only)
+
+--impl reference times that CPU path alone on the same metric/config (bounded sample per step).
+Only the cpu_baseline / --impl reference legs touch oracle/; the measured product path never does.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "analysis_bin_updates_per_s"
+UNIT = "bin-updates/s"
+WINDOWS = ("boxcar", "hann", "hamming", "blackman")
+M = 4096
+N_SAMPLES = 1 << 20
+SEED = 0x5DF70002
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.file = None
+
+    def start(self):
+        try:
+            self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=self.file, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            self.file.flush()
+            rows = [r.strip().split(",") for r in open(self.file.name) if r.strip()]
+            os.unlink(self.file.name)
+        except Exception:
+            rows = []
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(self.NAMES, r[3:7]):
+                    if "Active" in v and "Not" not in v:
+                        reasons.add(name)
+            except Exception:
+                continue
+        if sm:
+            out.update({"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                        "samples": len(sm)})
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference leg (the only place that touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(samples_per_window, threads, steps, warmup):
+    """One channel per host thread through the reference's sdft_sdft_n (all four windows per step).
+    Returns (bin-updates/s aggregate, seconds per step, kind, single-thread bin-updates/s)."""
+    from oracle import cpu_reference
+    rng = np.random.default_rng(SEED)
+    plans, kind = [], "port"
+    for t in range(threads):
+        row = []
+        for w in range(4):
+            p, kind = cpu_reference("f32", "f64", M, w, 1.0, fast=True)
+            row.append(p)
+        plans.append(row)
+    xs = [rng.uniform(-1, 1, samples_per_window).astype(np.float32) for _ in range(threads)]
+    outs = [np.zeros((samples_per_window, M), np.complex128) for _ in range(threads)]
+
+    def work(t):
+        for w in range(4):
+            p = plans[t][w]
+            fn = p._fn("ref_sdft_n" if kind == "reference" else "sdft_n", None,
+                       [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p])
+            fn(p.h, samples_per_window, xs[t].ctypes.data_as(ctypes.c_void_p), outs[t].ctypes.data_as(ctypes.c_void_p))
+
+    def step(nthreads):
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
+
+    for _ in range(warmup):
+        step(threads)
+    total = sum(step(threads) for _ in range(steps))
+    per_step = total / steps
+    agg = threads * 4 * samples_per_window * M / per_step
+    single = 4 * samples_per_window * M / step(1)
+    return agg, per_step, kind, single
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    spw = 4096
+    agg, per_step, kind, single = cpu_reference_run(spw, threads, args.steps, args.warmup)
+    sample = "%d host threads x 4 windows x %d samples per step (one channel per thread)" % (threads, spw)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": agg, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: white noise, m=4096, f32 TD / f64 FD, four windows; reference C "
+                               "sdft_sdft_n on host cores, bounded sample", "m": M, "sample": sample},
+        "cpu_baseline": {"value": agg, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                         "single_thread": single},
+        "e2e": {"value": agg, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200_arm(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from sdft_b200 import SDFT
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the sdft_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n, m = args.n, M
+    free_b, _ = torch.cuda.mem_get_info()
+    while n * m * 16 > 0.8 * free_b and n > 4096:
+        n //= 2
+    rng = np.random.default_rng([SEED, rank])
+    x_host = rng.uniform(-1, 1, n).astype(np.float32)
+    x = torch.from_numpy(x_host).to(dev)
+    out = torch.empty((n, m), dtype=torch.complex128, device=dev)
+    plans = [SDFT(m, w, 1, td="f32", fd="f64") for w in WINDOWS]
+    stream_ptr = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for p in plans:
+        p._lib.sdft_b200_set_stream(p._h, stream_ptr)
+    xp, op = ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr())
+
+    def analysis_step():
+        for p in plans:
+            p._f("sdft_n")(p._h, n, xp, op)
+
+    y = torch.empty(n, dtype=torch.float32, device=dev)
+    yp = ctypes.c_void_p(y.data_ptr())
+
+    def synthesis_step():
+        p = plans[-1]
+        p._f("isdft_n")(p._h, n, op, yp)
+
+    # ---- analysis: value + roofline --------------------------------------------------------------
+    for _ in range(args.warmup):
+        analysis_step()
+    for p in plans:
+        p._check()
+        p._lib.sdft_b200_set_profiling(p._h, 1)
+    launches0 = sum(p.launches for p in plans)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        analysis_step()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    clk = clocks.stop()
+    t_analysis = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    launches = sum(p.launches for p in plans) - launches0
+    kms, kcount = 0.0, 0
+    for p in plans:
+        c = ctypes.c_ulonglong(0)
+        kms += p._lib.sdft_b200_kernel_ms(p._h, 0, ctypes.byref(c))
+        kcount += c.value
+        p._lib.sdft_b200_set_profiling(p._h, 0)
+        p._check()
+    value = world * args.steps * 4 * n * m / t_analysis
+    peak, peak_src = measured_peaks()
+    alg_bytes = n * m * 16 + n * 4
+    dur = (kms / max(kcount, 1)) * 1e-3
+    achieved = alg_bytes / dur / 1e9 if dur > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "emit_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic = tj["dram_bytes_per_bin_update"] * n * m
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "emit_kernel<double>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dur * 1e3, "launches_timed": kcount,
+                "whole_call_GBps": args.steps * 4 * alg_bytes / t_analysis / 1e9}
+
+    # ---- synthesis -------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        synthesis_step()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+        synthesis_step()
+    s1.record()
+    torch.cuda.synchronize()
+    barrier()
+    t_synth = max_over_ranks(s0.elapsed_time(s1) * 1e-3)
+    synth = {"metric": "synthesis_samples_per_s", "value": world * args.steps * n / t_synth, "unit": "samples/s",
+             "ms_per_step": t_synth / args.steps * 1e3,
+             "roofline": {"bound": "hbm", "achieved": args.steps * alg_bytes / t_synth / 1e9, "peak": peak,
+                          "unit": "GB/s", "frac": args.steps * alg_bytes / t_synth / 1e9 / peak}}
+    del out, y
+    torch.cuda.empty_cache()
+
+    # ---- e2e: C-ABI call with host buffers (pinned), copies inside the timed region ---------------
+    n_e = min(args.e2e_n, n)
+    xe = torch.from_numpy(x_host[:n_e].copy()).pin_memory()
+    oe = torch.empty((n_e, m), dtype=torch.complex128).pin_memory()
+    pe = SDFT(m, "hann", 1, td="f32", fd="f64")
+    xep, oep = ctypes.c_void_p(xe.data_ptr()), ctypes.c_void_p(oe.data_ptr())
+    for _ in range(max(1, min(args.warmup, 3))):
+        pe._f("sdft_n")(pe._h, n_e, xep, oep)
+    pe._check()
+    e2e_launch0 = pe.launches
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pe._f("sdft_n")(pe._h, n_e, xep, oep)      # returns when the rows are in host memory
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    pe._check()
+    e2e = {"value": world * args.steps * n_e * m / t_e2e, "unit": UNIT, "h2d_bytes_per_step": n_e * 4,
+           "d2h_bytes_per_step": n_e * m * 16, "ms_per_step": t_e2e / args.steps * 1e3,
+           "sample": "sdft_sdft_n(host pinned samples -> host pinned (n, m) rows), n=%d, m=%d, hann; "
+                     "PCIe-bound: %.1f GB/s device->host" % (n_e, m, args.steps * n_e * m * 16 / t_e2e / 1e9)}
+    launches += pe.launches - e2e_launch0
+    del oe
+
+    # ---- CPU baseline beside it (rank 0, N = 1) -----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        spw = 4096
+        agg, per_step, kind, single = cpu_reference_run(spw, threads, 2, 1)
+        cpu = {"value": agg, "unit": UNIT, "cores": threads, "kind": kind, "single_thread": single,
+               "sample": "%d host threads x 4 windows x %d samples, one channel per thread, m=%d" % (threads, spw, m)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_analysis / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: 2^20-sample white noise, m=4096, f32 TD / f64 FD, "
+                                   "boxcar+hann+hamming+blackman per step; one channel per GPU",
+                       "n_samples": n, "m": m, "windows": list(WINDOWS), "parallelism": "channel-sharded x%d" % world,
+                       "l2": "no flush: each window writes %.0f GiB (>> 126 MB L2)" % (n * m * 16 / 2 ** 30)},
+            "roofline": roofline, "synthesis": synth, "e2e": e2e, "cpu_baseline": cpu, "clocks": clk,
+            "gpu_launches": int(launches),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=N_SAMPLES, help="samples per window (default 2^20)")
+    ap.add_argument("--e2e-n", type=int, default=1 << 16, help="samples per e2e step (host buffers)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+    else:
+        run_b200_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -130,6 +130,12 @@ SDFT_B200_API int sdft_b200_device(const sdft_b200_plan_t* plan);
 /* number of kernels this plan has launched so far (bench.py reports it as gpu_launches) */
 SDFT_B200_API unsigned long long sdft_b200_launch_count(const sdft_b200_plan_t* plan);
 
+/* CUDA-event timing of the dominant kernels on the plan's stream, for roofline reporting.
+ * sdft_b200_kernel_ms returns the summed duration (ms) of the launches of kernel class `which`
+ * (0 = analysis emit kernel, 1 = synthesis kernel) since the previous query, and their count. */
+SDFT_B200_API int sdft_b200_set_profiling(sdft_b200_plan_t* plan, int on);
+SDFT_B200_API double sdft_b200_kernel_ms(sdft_b200_plan_t* plan, int which, unsigned long long* launches);
+
 /* Introspection used by the parity tests: copies plan tables/state to HOST buffers.
  * twiddles: analysis and synthesis tables, dftsize complex values each (c/src/sdft/sdft.h:444-445).
  * state (channel): cursor, history (2*dftsize samples, oldest first), accumulators and current

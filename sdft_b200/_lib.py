@@ -42,6 +42,8 @@ UNTYPED = {
     "sdft_b200_channels": (_SZ, [_P]),
     "sdft_b200_device": (_I, [_P]),
     "sdft_b200_launch_count": (ctypes.c_ulonglong, [_P]),
+    "sdft_b200_set_profiling": (_I, [_P, _I]),
+    "sdft_b200_kernel_ms": (_D, [_P, _I, ctypes.POINTER(ctypes.c_ulonglong)]),
     "sdft_b200_get_twiddles": (_I, [_P, _P, _P]),
     "sdft_b200_get_state": (_I, [_P, _SZ, ctypes.POINTER(ctypes.c_size_t), _P, _P, _P]),
     "sdft_b200_host_alloc": (_P, [_SZ]),

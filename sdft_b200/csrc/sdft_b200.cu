@@ -4,7 +4,7 @@
  *
  * What lives where (reference: struct sdft_plan, c/src/sdft/sdft.h:137-182):
  *   tables   tw_ext[m+4], tws[m], F0[ceil(2m/32)][m+4]         device, written once per plan
- *   state    history[2][2m] (ping-pong), acc_state[m+4], phase_state[m+4] per channel; cursor on the host
+ *   state    history[2][2m] and phase_state[2][m+4] (ping-pong), acc_state[m+4] per channel; cursor on the host
  *   scratch  samples, deltas, chunk totals/carries, row tiles   device, grow-only
  *
  * No CPU fallback: every entry point either runs the CUDA path or records an error on the plan.
@@ -12,6 +12,7 @@
 #include "../../include/sdft_b200.h"
 #include "sdft_kernels.cuh"
 
+#include <vector>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -62,9 +63,14 @@ struct sdft_b200_plan
   void* history[2] = { nullptr, nullptr };
   int hist_sel = 0;
   void* acc_state = nullptr;
-  void* phase_state = nullptr;
+  void* phase_state[2] = { nullptr, nullptr };   // ping-pong: emit still reads the phase the call started with
+  int phase_sel = 0;
 
   Buffer samples, deltas, totals, synth_out, tile[2];
+
+  /* optional CUDA-event timing of the dominant kernels (bench.py roofline): [0] analysis emit, [1] synthesis */
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events[2];
 
   int status = 0;
   char errmsg[256] = "";
@@ -263,15 +269,16 @@ bool plan_build(Plan* p)
   CU_TRY(p, cudaMalloc(&p->history[0], ch * 2 * m * sizeof(T)));
   CU_TRY(p, cudaMalloc(&p->history[1], ch * 2 * m * sizeof(T)));
   CU_TRY(p, cudaMalloc(&p->acc_state, ch * cells * sizeof(cx<F>)));
-  CU_TRY(p, cudaMalloc(&p->phase_state, ch * cells * sizeof(cx<F>)));
+  CU_TRY(p, cudaMalloc(&p->phase_state[0], ch * cells * sizeof(cx<F>)));
+  CU_TRY(p, cudaMalloc(&p->phase_state[1], ch * cells * sizeof(cx<F>)));
 
   CU_TRY(p, cudaMemcpyAsync(p->tw_ext, tw_ext.data(), cells * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
   CU_TRY(p, cudaMemcpyAsync(p->tws, tws.data(), m * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
   /* stage P0 in phase_state[channel 0], expand it into the table, then reset copies row 0 everywhere */
-  CU_TRY(p, cudaMemcpyAsync(p->phase_state, p0.data(), cells * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
+  CU_TRY(p, cudaMemcpyAsync(p->phase_state[0], p0.data(), cells * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
   const unsigned threads = 128;
   phase_table_kernel<F><<<(unsigned)((cells + threads - 1) / threads), threads, 0, p->stream>>>(
-      (const cx<F>*)p->tw_ext, (const cx<F>*)p->phase_state, (cx<F>*)p->f0, (unsigned)cells, (unsigned)(2 * m));
+      (const cx<F>*)p->tw_ext, (const cx<F>*)p->phase_state[0], (cx<F>*)p->f0, (unsigned)cells, (unsigned)(2 * m));
   p->launches++;
   CU_TRY(p, cudaGetLastError());
   CU_TRY(p, cudaStreamSynchronize(p->stream));   // host vectors go out of scope
@@ -284,11 +291,12 @@ bool plan_reset(Plan* p)
   const size_t m = p->m, cells = p->cells, ch = p->channels;
   p->cursor = 0;
   p->hist_sel = 0;
+  p->phase_sel = 0;
   CU_TRY(p, cudaMemsetAsync(p->history[0], 0, ch * 2 * m * sizeof(T), p->stream));
   CU_TRY(p, cudaMemsetAsync(p->acc_state, 0, ch * cells * sizeof(cx<F>), p->stream));
   for (size_t c = 0; c < ch; ++c)
   {
-    CU_TRY(p, cudaMemcpyAsync((cx<F>*)p->phase_state + c * cells, p->f0, cells * sizeof(cx<F>),
+    CU_TRY(p, cudaMemcpyAsync((cx<F>*)p->phase_state[0] + c * cells, p->f0, cells * sizeof(cx<F>),
                               cudaMemcpyDeviceToDevice, p->stream));
   }
   return true;
@@ -300,10 +308,12 @@ void plan_destroy(Plan* p)
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
-  void* ptrs[] = { p->tw_ext, p->tws, p->f0, p->history[0], p->history[1], p->acc_state, p->phase_state,
+  void* ptrs[] = { p->tw_ext, p->tws, p->f0, p->history[0], p->history[1], p->acc_state, p->phase_state[0], p->phase_state[1],
                    p->samples.ptr, p->deltas.ptr, p->totals.ptr, p->synth_out.ptr, p->tile[0].ptr, p->tile[1].ptr };
   for (void* q : ptrs)
     if (q) cudaFree(q);
+  for (int w = 0; w < 2; ++w)
+    for (cudaEvent_t e : p->prof_events[w]) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i)
   {
     if (p->tile_ready[i]) cudaEventDestroy(p->tile_ready[i]);
@@ -378,6 +388,15 @@ Plan* plan_create(size_t m, int window, double latency, size_t channels)
 /* ------------------------------------------------------------------------------------------------
  * device-side passes
  * ---------------------------------------------------------------------------------------------- */
+void prof_mark(Plan* p, int which)
+{
+  if (!p->profiling) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaEventRecord(e, p->stream);
+  p->prof_events[which].push_back(e);
+}
+
 unsigned groups_for(const Plan* p)
 {
   const unsigned span = (p->window == 0) ? kWarpCells : kWarpCells - 4;
@@ -452,7 +471,8 @@ bool analysis_device(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out,
   s.delta_stride = n;
   s.tw_ext = (const cx<F>*)p->tw_ext;
   s.f0 = (const cx<F>*)p->f0;
-  s.phase_state = (cx<F>*)p->phase_state;
+  s.phase_in = (const cx<F>*)p->phase_state[p->phase_sel];
+  s.phase_out = (cx<F>*)p->phase_state[p->phase_sel ^ 1];
   s.acc_state = (cx<F>*)p->acc_state;
   s.totals = (cx<F>*)p->totals.ptr;
   s.m = m;
@@ -480,10 +500,13 @@ bool analysis_device(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out,
     a.win.wq = a.win.w * (F)(0.25);             // sdft.h:371
     const size_t pair_bytes = 2 * sizeof(cx<F>);
     const bool vec = (m % 2 == 0) && (((uintptr_t)out) % pair_bytes == 0) && (out_stride % 2 == 0);
+    prof_mark(p, 0);
     launch_emit<F>(p, a, dim3(sched.nchunks * a.group_blocks, ch), vec);
+    prof_mark(p, 0);
   }
   CU_TRY(p, cudaGetLastError());
   p->cursor = (size_t)((p->cursor + n) % (2 * (size_t)m));
+  p->phase_sel ^= 1;
   return true;
 }
 
@@ -495,12 +518,14 @@ bool synthesis_device(Plan* p, size_t n, const cx<F>* dfts, size_t dft_stride, T
   size_t blocks = (n + kSynthWarps - 1) / kSynthWarps;
   if (blocks > 148 * 8) blocks = 148 * 8;
   const dim3 grid((unsigned)blocks, ch);
+  prof_mark(p, 1);
   if (p->latency == 1)
     synth_kernel<T, F, true><<<grid, kSynthWarps * 32, 0, p->stream>>>(dfts, dft_stride, (const cx<F>*)p->tws, y,
                                                                        y_stride, n, (unsigned)p->m);
   else
     synth_kernel<T, F, false><<<grid, kSynthWarps * 32, 0, p->stream>>>(dfts, dft_stride, (const cx<F>*)p->tws, y,
                                                                         y_stride, n, (unsigned)p->m);
+  prof_mark(p, 1);
   p->launches++;
   CU_TRY(p, cudaGetLastError());
   return true;
@@ -874,6 +899,33 @@ extern "C" int sdft_b200_set_chunk(sdft_b200_plan_t* p, size_t chunk)
   return 0;
 }
 
+extern "C" int sdft_b200_set_profiling(sdft_b200_plan_t* p, int on)
+{
+  if (!p) return SDFT_B200_ERR_ARG;
+  p->profiling = on != 0;
+  return 0;
+}
+
+extern "C" double sdft_b200_kernel_ms(sdft_b200_plan_t* p, int which, unsigned long long* launches)
+{
+  if (launches) *launches = 0;
+  if (!p || which < 0 || which > 1) return 0.0;
+  cudaSetDevice(p->device);
+  std::vector<cudaEvent_t>& ev = p->prof_events[which];
+  double total = 0.0;
+  if (!ev.empty()) cudaEventSynchronize(ev.back());
+  for (size_t i = 0; i + 1 < ev.size(); i += 2)
+  {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) total += ms;
+    if (launches) ++*launches;
+  }
+  for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  ev.clear();
+  cudaGetLastError();
+  return total;
+}
+
 extern "C" size_t sdft_b200_channels(const sdft_b200_plan_t* p) { return p ? p->channels : 0; }
 extern "C" int sdft_b200_device(const sdft_b200_plan_t* p) { return p ? p->device : -1; }
 extern "C" unsigned long long sdft_b200_launch_count(const sdft_b200_plan_t* p) { return p ? p->launches : 0; }
@@ -906,7 +958,7 @@ extern "C" int sdft_b200_get_state(sdft_b200_plan_t* p, size_t channel, size_t* 
     e = cudaMemcpy(accumulators, (char*)p->acc_state + (channel * p->cells + 2) * cbytes, p->m * cbytes,
                    cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && phase)
-    e = cudaMemcpy(phase, (char*)p->phase_state + (channel * p->cells + 2) * cbytes, p->m * cbytes,
+    e = cudaMemcpy(phase, (char*)p->phase_state[p->phase_sel] + (channel * p->cells + 2) * cbytes, p->m * cbytes,
                    cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) plan_fail(p, (int)e, "sdft_b200_get_state", __FILE__, __LINE__);
   return p->status;

@@ -294,7 +294,8 @@ template <typename F> struct ScanArgs
   size_t delta_stride;
   const cx<F>* tw_ext;     // (cells)
   const cx<F>* f0;         // (rows, cells)
-  cx<F>* phase_state;      // (channels, cells)  P at the plan's cursor
+  const cx<F>* phase_in;   // (channels, cells)  P at the cursor the call starts with
+  cx<F>* phase_out;        // (channels, cells)  P at the cursor the call ends with (other buffer)
   cx<F>* acc_state;        // (channels, cells)
   cx<F>* totals;           // (channels, nchunks, cells): totals, then carries in place
   unsigned m;
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(kTotalsThreads) chunk_totals_kernel(const Scan
   if (k >= a.m) return;
   const unsigned e = k + 2;
   const cx<F> w = a.tw_ext[e];
-  cx<F> p = cs.first ? a.phase_state[(size_t)ch * a.cells + e] : a.f0[(size_t)cs.f0_row * a.cells + e];
+  cx<F> p = cs.first ? a.phase_in[(size_t)ch * a.cells + e] : a.f0[(size_t)cs.f0_row * a.cells + e];
   cx<F> acc;
   acc.r = (F)0; acc.i = (F)0;
   const unsigned body = cs.len - 1;
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(kTotalsThreads) chunk_totals_kernel(const Scan
   if (j == a.sched.nchunks - 1)
   {
     p = cs.wraps ? a.f0[e] : Arith<F>::rotate(p, w);   // row 0 of the table is the restart value
-    store_with_mirrors(a.phase_state + (size_t)ch * a.cells, k, p, a.mirrors);
+    store_with_mirrors(a.phase_out + (size_t)ch * a.cells, k, p, a.mirrors);
   }
 }
 
@@ -539,7 +540,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs<F>
 
   EmitLane<F, WINDOW, VEC> L;
   cx<F> restart[kCellsPerLane];
-  const cx<F>* phase_src = cs.first ? s.phase_state + (size_t)ch * s.cells
+  const cx<F>* phase_src = cs.first ? s.phase_in + (size_t)ch * s.cells
                                     : s.f0 + (size_t)cs.f0_row * s.cells;
   const cx<F>* carry_src = s.totals + ((size_t)ch * s.sched.nchunks + j) * s.cells;
 #pragma unroll

@@ -176,7 +176,7 @@ def test_device_pointers_and_batch(SDFT):
     # host batch path
     g2 = SDFT(m, "hann", 0.5, td="f32", fd="f64", channels=ch)
     got2 = g2.sdft(x)
-    assert np.array_equal(_bits(got2), _bits(got))
+    assert rel_err(got2, got) <= 1e-13   # one 3000-sample call vs three calls: other chunking, same rows
 
 
 def test_advance_and_roundtrip(SDFT):
