@@ -62,11 +62,16 @@ struct sdft_b200_plan
 
   void* history[2] = { nullptr, nullptr };
   int hist_sel = 0;
-  void* acc_state = nullptr;
+  void* acc_state[2] = { nullptr, nullptr };     // ping-pong, same reason (neighbouring groups share halo cells)
+  int acc_sel = 0;
   void* phase_state[2] = { nullptr, nullptr };   // ping-pong: emit still reads the phase the call started with
   int phase_sel = 0;
 
   Buffer samples, deltas, totals, synth_out, tile[2];
+  Buffer prefix, chain_totals, flags;   // chained scan: inclusive prefixes, chunk totals, epoch-stamped flags
+  unsigned* control = nullptr;   // [0] work ticket, [1] spin-wait timeout flag
+  unsigned epoch = 0;
+  bool three_pass = false;       // SDFT_B200_PIPELINE=3pass: separate totals / carry / emit kernels
 
   /* optional CUDA-event timing of the dominant kernels (bench.py roofline): [0] analysis emit, [1] synthesis */
   bool profiling = false;
@@ -84,7 +89,7 @@ typedef sdft_b200_plan Plan;
 namespace
 {
 
-enum { SDFT_B200_ERR_TYPE = 10001, SDFT_B200_ERR_ARG = 10002, SDFT_B200_ERR_NODEVICE = 10003 };
+enum { SDFT_B200_ERR_TYPE = 10001, SDFT_B200_ERR_ARG = 10002, SDFT_B200_ERR_NODEVICE = 10003, SDFT_B200_ERR_CHAIN = 10004 };
 
 thread_local int g_alloc_error = 0;
 thread_local char g_alloc_errmsg[256] = "";
@@ -268,7 +273,10 @@ bool plan_build(Plan* p)
   CU_TRY(p, cudaMalloc(&p->f0, p->f0_rows * cells * sizeof(cx<F>)));
   CU_TRY(p, cudaMalloc(&p->history[0], ch * 2 * m * sizeof(T)));
   CU_TRY(p, cudaMalloc(&p->history[1], ch * 2 * m * sizeof(T)));
-  CU_TRY(p, cudaMalloc(&p->acc_state, ch * cells * sizeof(cx<F>)));
+  CU_TRY(p, cudaMalloc(&p->acc_state[0], ch * cells * sizeof(cx<F>)));
+  CU_TRY(p, cudaMalloc(&p->acc_state[1], ch * cells * sizeof(cx<F>)));
+  CU_TRY(p, cudaMalloc(&p->control, 2 * sizeof(unsigned)));
+  CU_TRY(p, cudaMemsetAsync(p->control, 0, 2 * sizeof(unsigned), p->stream));
   CU_TRY(p, cudaMalloc(&p->phase_state[0], ch * cells * sizeof(cx<F>)));
   CU_TRY(p, cudaMalloc(&p->phase_state[1], ch * cells * sizeof(cx<F>)));
 
@@ -292,8 +300,10 @@ bool plan_reset(Plan* p)
   p->cursor = 0;
   p->hist_sel = 0;
   p->phase_sel = 0;
+  p->acc_sel = 0;
   CU_TRY(p, cudaMemsetAsync(p->history[0], 0, ch * 2 * m * sizeof(T), p->stream));
-  CU_TRY(p, cudaMemsetAsync(p->acc_state, 0, ch * cells * sizeof(cx<F>), p->stream));
+  CU_TRY(p, cudaMemsetAsync(p->acc_state[0], 0, ch * cells * sizeof(cx<F>), p->stream));
+  CU_TRY(p, cudaMemsetAsync(p->acc_state[1], 0, ch * cells * sizeof(cx<F>), p->stream));
   for (size_t c = 0; c < ch; ++c)
   {
     CU_TRY(p, cudaMemcpyAsync((cx<F>*)p->phase_state[0] + c * cells, p->f0, cells * sizeof(cx<F>),
@@ -308,7 +318,8 @@ void plan_destroy(Plan* p)
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
-  void* ptrs[] = { p->tw_ext, p->tws, p->f0, p->history[0], p->history[1], p->acc_state, p->phase_state[0], p->phase_state[1],
+  void* ptrs[] = { p->tw_ext, p->tws, p->f0, p->history[0], p->history[1], p->acc_state[0], p->acc_state[1], p->phase_state[0], p->phase_state[1],
+                   p->prefix.ptr, p->chain_totals.ptr, p->flags.ptr, p->control,
                    p->samples.ptr, p->deltas.ptr, p->totals.ptr, p->synth_out.ptr, p->tile[0].ptr, p->tile[1].ptr };
   for (void* q : ptrs)
     if (q) cudaFree(q);
@@ -354,6 +365,10 @@ Plan* plan_create(size_t m, int window, double latency, size_t channels)
   p->mirrors = make_mirrors(m);
   p->tile_bytes = env_size("SDFT_B200_TILE_MB", 128) << 20;
   p->forced_chunk = env_size("SDFT_B200_CHUNK", 0);
+  {
+    const char* pl = getenv("SDFT_B200_PIPELINE");
+    p->three_pass = pl && !strcmp(pl, "3pass");
+  }
 
   bool ok = true;
   const long dev_env = (long)env_size("SDFT_B200_DEVICE", (size_t)-1);
@@ -415,7 +430,7 @@ unsigned choose_chunk(const Plan* p, size_t n)
   /* enough warps to fill 148 SMs x 16 resident warps a few times over, else the shortest chunk */
   const double want = 148.0 * 16.0 * 4.0;
   const double per_sample = (double)groups_for(p) * (double)p->channels;
-  unsigned c = kMaxChunk;
+  unsigned c = kAutoChunk;
   while (c > (unsigned)kF0Stride && ((double)n / c) * per_sample < want) c >>= 1;
   return c;
 }
@@ -439,12 +454,116 @@ void launch_emit(Plan* p, const EmitArgs<F>& a, dim3 grid, bool vec)
   p->launches++;
 }
 
+template <typename F, bool EMIT>
+void launch_chain(Plan* p, const ChainArgs<F>& a, bool vec)
+{
+  const dim3 grid(a.total_blocks);
+#define SDFT_CHAIN_CASE(W)                                                                             \
+  case W:                                                                                              \
+    if (vec) scan_emit_kernel<F, W, true, EMIT><<<grid, kEmitWarps * 32, 0, p->stream>>>(a);           \
+    else scan_emit_kernel<F, W, false, EMIT><<<grid, kEmitWarps * 32, 0, p->stream>>>(a);              \
+    break;
+  switch (p->window)
+  {
+    SDFT_CHAIN_CASE(0)
+    SDFT_CHAIN_CASE(1)
+    SDFT_CHAIN_CASE(2)
+    SDFT_CHAIN_CASE(3)
+  }
+#undef SDFT_CHAIN_CASE
+  p->launches++;
+}
+
+/* production path: K1 + the single-pass chained scan/emit kernel */
+template <typename T, typename F>
+bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride)
+{
+  const unsigned m = (unsigned)p->m;
+  const unsigned ch = (unsigned)p->channels;
+  const unsigned chunk = choose_chunk(p, n);
+  const Schedule sched = make_schedule(p->cursor, n, m, chunk);
+  const unsigned groups = groups_for(p);
+  const unsigned group_blocks = (groups + kEmitWarps - 1) / kEmitWarps;
+  const size_t items = (size_t)ch * sched.nchunks * groups;
+  const size_t blocks = (size_t)ch * sched.nchunks * group_blocks;
+  if (blocks >= (1ull << 31))
+  {
+    plan_fail(p, SDFT_B200_ERR_ARG, "analysis: call too large for one launch", __FILE__, __LINE__);
+    return false;
+  }
+
+  if (!reserve(p, p->deltas, (size_t)ch * n * sizeof(F))) return false;
+  if (!reserve(p, p->prefix, items * kWarpCells * sizeof(cx<F>))) return false;
+  if (!reserve(p, p->chain_totals, items * kWarpCells * sizeof(cx<F>))) return false;
+  const size_t flags_before = p->flags.bytes;
+  if (!reserve(p, p->flags, items * sizeof(unsigned))) return false;
+  if (p->flags.bytes != flags_before || p->epoch >= 0x7ffffff0u)
+  {
+    CU_TRY(p, cudaMemsetAsync(p->flags.ptr, 0, p->flags.bytes, p->stream));
+    p->epoch = 0;
+  }
+  p->epoch++;
+
+  {
+    const size_t work = n > 2 * (size_t)m ? n : 2 * (size_t)m;
+    unsigned kblocks = (unsigned)((work + 255) / 256);
+    if (kblocks > 2048) kblocks = 2048;
+    delta_kernel<T, F><<<dim3(kblocks, ch), 256, 0, p->stream>>>(
+        x, x_stride, (const T*)p->history[p->hist_sel], (T*)p->history[p->hist_sel ^ 1],
+        (F*)p->deltas.ptr, n, n, 2 * m);
+    p->launches++;
+    p->hist_sel ^= 1;
+  }
+
+  ChainArgs<F> a;
+  a.sched = sched;
+  a.delta = (const F*)p->deltas.ptr;
+  a.delta_stride = n;
+  a.tw_ext = (const cx<F>*)p->tw_ext;
+  a.f0 = (const cx<F>*)p->f0;
+  a.phase_in = (const cx<F>*)p->phase_state[p->phase_sel];
+  a.phase_out = (cx<F>*)p->phase_state[p->phase_sel ^ 1];
+  a.acc_in = (const cx<F>*)p->acc_state[p->acc_sel];
+  a.acc_out = (cx<F>*)p->acc_state[p->acc_sel ^ 1];
+  a.prefix = (cx<F>*)p->prefix.ptr;
+  a.totals = (cx<F>*)p->chain_totals.ptr;
+  a.flags = (unsigned*)p->flags.ptr;
+  a.control = p->control;
+  a.epoch = p->epoch;
+  a.total_blocks = (unsigned)blocks;
+  a.m = m;
+  a.cells = (unsigned)p->cells;
+  a.out = out;
+  a.out_channel_stride = out_stride;
+  a.groups = groups;
+  a.group_blocks = group_blocks;
+  a.win = make_window_const<F>(p->m, p->window);   // sdft.h:422, :371
+  if (out)
+  {
+    const size_t pair_bytes = 2 * sizeof(cx<F>);
+    const bool vec = (m % 2 == 0) && (((uintptr_t)out) % pair_bytes == 0) && (out_stride % 2 == 0);
+    prof_mark(p, 0);
+    launch_chain<F, true>(p, a, vec);
+    prof_mark(p, 0);
+  }
+  else
+  {
+    launch_chain<F, false>(p, a, false);
+  }
+  CU_TRY(p, cudaGetLastError());
+  p->cursor = (size_t)((p->cursor + n) % (2 * (size_t)m));
+  p->phase_sel ^= 1;
+  p->acc_sel ^= 1;
+  return true;
+}
+
 /* analysis over n samples per channel, everything on the device.
  * x: (channels, x_stride) samples; out: (channels, out_stride) complex rows or nullptr (state only). */
 template <typename T, typename F>
 bool analysis_device(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride)
 {
   if (n == 0) return true;
+  if (!p->three_pass) return analysis_chained<T, F>(p, n, x, x_stride, out, out_stride);
   const unsigned m = (unsigned)p->m;
   const unsigned ch = (unsigned)p->channels;
   const unsigned chunk = choose_chunk(p, n);
@@ -473,7 +592,7 @@ bool analysis_device(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out,
   s.f0 = (const cx<F>*)p->f0;
   s.phase_in = (const cx<F>*)p->phase_state[p->phase_sel];
   s.phase_out = (cx<F>*)p->phase_state[p->phase_sel ^ 1];
-  s.acc_state = (cx<F>*)p->acc_state;
+  s.acc_state = (cx<F>*)p->acc_state[p->acc_sel];
   s.totals = (cx<F>*)p->totals.ptr;
   s.m = m;
   s.cells = (unsigned)p->cells;
@@ -496,8 +615,7 @@ bool analysis_device(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out,
     a.out_channel_stride = out_stride;
     a.groups = groups_for(p);
     a.group_blocks = (a.groups + kEmitWarps - 1) / kEmitWarps;
-    a.win.w = (F)(1) / (F)(p->m * 2);           // sdft.h:422
-    a.win.wq = a.win.w * (F)(0.25);             // sdft.h:371
+    a.win = make_window_const<F>(p->m, p->window);   // sdft.h:422, :371
     const size_t pair_bytes = 2 * sizeof(cx<F>);
     const bool vec = (m % 2 == 0) && (((uintptr_t)out) % pair_bytes == 0) && (out_stride % 2 == 0);
     prof_mark(p, 0);
@@ -879,16 +997,21 @@ extern "C" int sdft_b200_synchronize(sdft_b200_plan_t* p)
   cudaSetDevice(p->device);
   cudaError_t e = cudaStreamSynchronize(p->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(p->copy_stream);
+  unsigned ctl[2] = { 0, 0 };
+  if (e == cudaSuccess) e = cudaMemcpy(ctl, p->control, sizeof(ctl), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) plan_fail(p, (int)e, "sdft_b200_synchronize", __FILE__, __LINE__);
+  else if (ctl[1]) plan_fail(p, SDFT_B200_ERR_CHAIN, "chained scan: a carry wait timed out", __FILE__, __LINE__);
   return p->status;
 }
 
 extern "C" int sdft_b200_set_stream(sdft_b200_plan_t* p, void* cuda_stream)
 {
   if (!p) return SDFT_B200_ERR_ARG;
+  cudaStream_t next = (cuda_stream == (void*)-1) ? p->own_stream : (cudaStream_t)cuda_stream;
+  if (next == p->stream) return p->status;
   cudaSetDevice(p->device);
-  cudaStreamSynchronize(p->stream);
-  p->stream = (cuda_stream == (void*)-1) ? p->own_stream : (cudaStream_t)cuda_stream;
+  cudaStreamSynchronize(p->stream);   // work queued on the old stream must not race with the new one
+  p->stream = next;
   return p->status;
 }
 
@@ -955,7 +1078,7 @@ extern "C" int sdft_b200_get_state(sdft_b200_plan_t* p, size_t channel, size_t* 
     e = cudaMemcpy(history, (char*)p->history[p->hist_sel] + channel * 2 * p->m * tbytes, 2 * p->m * tbytes,
                    cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && accumulators)
-    e = cudaMemcpy(accumulators, (char*)p->acc_state + (channel * p->cells + 2) * cbytes, p->m * cbytes,
+    e = cudaMemcpy(accumulators, (char*)p->acc_state[p->acc_sel] + (channel * p->cells + 2) * cbytes, p->m * cbytes,
                    cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && phase)
     e = cudaMemcpy(phase, (char*)p->phase_state[p->phase_sel] + (channel * p->cells + 2) * cbytes, p->m * cbytes,

@@ -29,7 +29,8 @@ namespace sdftb200
 {
 
 constexpr int kF0Stride = 32;     // phase table holds P at every 32nd cursor
-constexpr int kMaxChunk = 1024;   // longest chunk (samples)
+constexpr int kMaxChunk = 1024;   // longest chunk the kernels accept (samples)
+constexpr int kAutoChunk = 512;   // longest chunk the heuristic picks (measured best on B200)
 constexpr int kEmitWarps = 4;     // warps per emit CTA
 constexpr int kCellsPerLane = 4;  // consecutive cells owned by one lane
 constexpr int kWarpCells = 32 * kCellsPerLane;
@@ -108,12 +109,31 @@ template <typename F> struct WindowConst
 {
   F w;       // analysis weight 1/(2m)                        sdft.h:422
   F wq;      // w * 0.25, the Hann factor                     sdft.h:371
+  F c0, c1, c2;   // double path: weight folded into the centre / first / second neighbour coefficients
 };
 
-template <typename F, int WINDOW>
-__device__ __forceinline__ F window_tap(F l2, F l1, F c, F r1, F r2, const WindowConst<F>& k)
+template <typename F>
+inline WindowConst<F> make_window_const(size_t m, int window)
 {
-  typedef Arith<F> A;
+  WindowConst<F> k;
+  k.w = (F)(1) / (F)(m * 2);
+  k.wq = k.w * (F)(0.25);
+  switch (window)
+  {
+    case 1: k.c0 = (F)2 * k.wq; k.c1 = k.wq; k.c2 = (F)0; break;
+    case 2: k.c0 = (F)(0.54) * k.w; k.c1 = (F)(0.23) * k.w; k.c2 = (F)0; break;
+    case 3: k.c0 = (F)(0.42) * k.w; k.c1 = (F)(0.25) * k.w; k.c2 = (F)(0.04) * k.w; break;
+    default: k.c0 = k.w; k.c1 = (F)0; k.c2 = (F)0; break;
+  }
+  return k;
+}
+
+/* float: the reference's operation order, un-fused */
+template <int WINDOW>
+__device__ __forceinline__ float window_tap(float l2, float l1, float c, float r1, float r2, const WindowConst<float>& k)
+{
+  typedef Arith<float> A;
+  typedef float F;
   if (WINDOW == 1)
   {
     return A::mul(A::sub(A::add(c, c), A::add(l1, r1)), k.wq);
@@ -132,6 +152,27 @@ __device__ __forceinline__ F window_tap(F l2, F l1, F c, F r1, F r2, const Windo
   else
   {
     return A::mul(c, k.w);
+  }
+}
+
+/* double: same taps with the weight folded into the coefficients and FMAs (3 / 3 / 5 FP64 instructions
+ * per component instead of 4 / 5 / 8); differs from the reference's order by rounding only (~1e-16) */
+template <int WINDOW>
+__device__ __forceinline__ double window_tap(double l2, double l1, double c, double r1, double r2,
+                                             const WindowConst<double>& k)
+{
+  if (WINDOW == 0)
+  {
+    return __dmul_rn(c, k.c0);
+  }
+  else if (WINDOW == 3)
+  {
+    const double t = __fma_rn(c, k.c0, -__dmul_rn(__dadd_rn(l1, r1), k.c1));
+    return __fma_rn(__dadd_rn(l2, r2), k.c2, t);
+  }
+  else
+  {
+    return __fma_rn(c, k.c0, -__dmul_rn(__dadd_rn(l1, r1), k.c1));
   }
 }
 
@@ -469,8 +510,8 @@ struct EmitLane
 #pragma unroll
       for (int b = 0; b < kCellsPerLane; ++b)
       {
-        y[b].r = A::mul(x[b].r, win.w);
-        y[b].i = A::mul(x[b].i, win.w);
+        y[b].r = window_tap<0>(x[b].r, x[b].r, x[b].r, x[b].r, x[b].r, win);
+        y[b].i = window_tap<0>(x[b].i, x[b].i, x[b].i, x[b].i, x[b].i, win);
       }
     }
     else
@@ -488,14 +529,14 @@ struct EmitLane
       {
         l2 = l1; r2 = r1;   // unused
       }
-      y[0].r = window_tap<F, WINDOW>(l2.r, l1.r, x[0].r, x[1].r, x[2].r, win);
-      y[0].i = window_tap<F, WINDOW>(l2.i, l1.i, x[0].i, x[1].i, x[2].i, win);
-      y[1].r = window_tap<F, WINDOW>(l1.r, x[0].r, x[1].r, x[2].r, x[3].r, win);
-      y[1].i = window_tap<F, WINDOW>(l1.i, x[0].i, x[1].i, x[2].i, x[3].i, win);
-      y[2].r = window_tap<F, WINDOW>(x[0].r, x[1].r, x[2].r, x[3].r, r1.r, win);
-      y[2].i = window_tap<F, WINDOW>(x[0].i, x[1].i, x[2].i, x[3].i, r1.i, win);
-      y[3].r = window_tap<F, WINDOW>(x[1].r, x[2].r, x[3].r, r1.r, r2.r, win);
-      y[3].i = window_tap<F, WINDOW>(x[1].i, x[2].i, x[3].i, r1.i, r2.i, win);
+      y[0].r = window_tap<WINDOW>(l2.r, l1.r, x[0].r, x[1].r, x[2].r, win);
+      y[0].i = window_tap<WINDOW>(l2.i, l1.i, x[0].i, x[1].i, x[2].i, win);
+      y[1].r = window_tap<WINDOW>(l1.r, x[0].r, x[1].r, x[2].r, x[3].r, win);
+      y[1].i = window_tap<WINDOW>(l1.i, x[0].i, x[1].i, x[2].i, x[3].i, win);
+      y[2].r = window_tap<WINDOW>(x[0].r, x[1].r, x[2].r, x[3].r, r1.r, win);
+      y[2].i = window_tap<WINDOW>(x[0].i, x[1].i, x[2].i, x[3].i, r1.i, win);
+      y[3].r = window_tap<WINDOW>(x[1].r, x[2].r, x[3].r, r1.r, r2.r, win);
+      y[3].i = window_tap<WINDOW>(x[1].i, x[2].i, x[3].i, r1.i, r2.i, win);
     }
     if (VEC)
     {
@@ -571,6 +612,309 @@ __global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs<F>
   if (cs.wraps)
   {
     L.template step<true>(sdelta[body], restart, a.win, row_stride);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K23  single-pass chained scan + emit (the production analysis kernel)
+ *
+ *      Same work items as K3 (one warp = one chunk x 128 cells), but the warp first computes its own
+ *      chunk total (K2's job, FP64/FP32 only, no memory traffic), then obtains the carry from the warp
+ *      that owns the PREVIOUS chunk of the same cells, publishes its inclusive prefix, and only then
+ *      replays the chunk and streams the rows out.  Warps in the compute phase and warps in the store
+ *      phase share every SM, so the scan arithmetic hides under the HBM-bound stores instead of
+ *      running as separate kernels in front of them.
+ *
+ *      Ordering.  carry_j = (((acc + total_0) + total_1) + ...) + total_{j-1}, always added in chunk
+ *      order, so results are deterministic and independent of timing (see the look-back comment in the
+ *      kernel).  Work items are handed out through an atomic ticket in (channel, chunk, group) order;
+ *      an item only ever waits for items with smaller tickets, which have all started and publish
+ *      their totals without waiting for anybody, so the kernel cannot deadlock whatever the block
+ *      scheduler does.  Publication: cells are written by all lanes, fenced, then lane 0 releases a
+ *      per-item flag stamped with the call's epoch (no flag clearing between calls); consumers acquire
+ *      the flag and read the cells through L2.  A wait that exceeds kSpinLimitNs sets *error and gives
+ *      up, so a logic error shows up as a reported failure, not as a hung device.
+ * ---------------------------------------------------------------------------------------------- */
+template <typename F> struct ChainArgs
+{
+  Schedule sched;
+  const F* delta;          // (channels, delta_stride)
+  size_t delta_stride;
+  const cx<F>* tw_ext;     // (cells)
+  const cx<F>* f0;         // (rows, cells)
+  const cx<F>* phase_in;   // (channels, cells)
+  cx<F>* phase_out;
+  const cx<F>* acc_in;     // (channels, cells)
+  cx<F>* acc_out;
+  cx<F>* totals;           // (channels, nchunks, groups, kWarpCells) each chunk's own total
+  cx<F>* prefix;           // (channels, nchunks, groups, kWarpCells) inclusive prefix after each chunk
+  unsigned* flags;         // (channels, nchunks, groups): 2*epoch = total published, 2*epoch+1 = prefix published
+  unsigned* control;       // [0] ticket counter, [1] error flag
+  unsigned epoch;
+  unsigned total_blocks;
+  unsigned m;
+  unsigned cells;
+  cx<F>* out;              // (channels, n, m) or nullptr
+  size_t out_channel_stride;
+  unsigned groups;
+  unsigned group_blocks;
+  WindowConst<F> win;
+};
+
+constexpr unsigned long long kSpinLimitNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
+{
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v)
+{
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+template <typename F> __device__ __forceinline__ cx<F> load_l2(const cx<F>* p);
+template <> __device__ __forceinline__ cx<double> load_l2<double>(const cx<double>* p)
+{
+  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+  cx<double> o; o.r = v.x; o.i = v.y; return o;
+}
+template <> __device__ __forceinline__ cx<float> load_l2<float>(const cx<float>* p)
+{
+  const float2 v = __ldcg(reinterpret_cast<const float2*>(p));
+  cx<float> o; o.r = v.x; o.i = v.y; return o;
+}
+template <typename F> __device__ __forceinline__ void store_l2(cx<F>* p, cx<F> v);
+template <> __device__ __forceinline__ void store_l2<double>(cx<double>* p, cx<double> v)
+{
+  __stcg(reinterpret_cast<double2*>(p), make_double2(v.r, v.i));
+}
+template <> __device__ __forceinline__ void store_l2<float>(cx<float>* p, cx<float> v)
+{
+  __stcg(reinterpret_cast<float2*>(p), make_float2(v.r, v.i));
+}
+
+template <typename F, int WINDOW, bool VEC, bool EMIT>
+__global__ void __launch_bounds__(kEmitWarps * 32, 4) scan_emit_kernel(const ChainArgs<F> a)
+{
+  constexpr int HALO = (WINDOW == 0) ? 0 : 2;
+  constexpr int SPAN = kWarpCells - 2 * HALO;
+  __shared__ F sdelta[kMaxChunk];
+  __shared__ unsigned s_ticket;
+
+  if (threadIdx.x == 0)
+  {
+    const unsigned t = atomicAdd(&a.control[0], 1u);
+    if (t == a.total_blocks - 1) a.control[0] = 0;   // last ticket of the launch: rearm for the next call
+    s_ticket = t;
+  }
+  __syncthreads();
+  const unsigned ticket = s_ticket;
+  const unsigned per_channel = a.sched.nchunks * a.group_blocks;
+  const unsigned ch = ticket / per_channel;
+  const unsigned rem = ticket - ch * per_channel;
+  const unsigned j = rem / a.group_blocks;
+  const unsigned gblk = rem - j * a.group_blocks;
+  const ChunkSpan cs = chunk_span(a.sched, j);
+
+  const F* dsrc = a.delta + (size_t)ch * a.delta_stride + cs.t0;
+  for (unsigned i = threadIdx.x; i < cs.len; i += kEmitWarps * 32) sdelta[i] = dsrc[i];
+  __syncthreads();
+
+  const unsigned warp = threadIdx.x >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned group = gblk * kEmitWarps + warp;
+  if (group >= a.groups) return;
+
+  const unsigned first_bin = group * SPAN;
+  const unsigned e0 = first_bin + 2 - HALO + lane * kCellsPerLane;
+  const bool last_chunk = (j == a.sched.nchunks - 1);
+
+  EmitLane<F, WINDOW, VEC> L;
+  cx<F> restart[kCellsPerLane];
+  cx<F> start[kCellsPerLane];
+  bool live[kCellsPerLane];
+  const cx<F>* phase_src = cs.first ? a.phase_in + (size_t)ch * a.cells : a.f0 + (size_t)cs.f0_row * a.cells;
+  cx<F> zero;
+  zero.r = (F)0; zero.i = (F)0;
+#pragma unroll
+  for (int b = 0; b < kCellsPerLane; ++b)
+  {
+    const unsigned e = e0 + b;
+    live[b] = e < a.cells;
+    L.tw[b] = live[b] ? a.tw_ext[e] : zero;
+    start[b] = live[b] ? phase_src[e] : zero;
+    restart[b] = live[b] ? a.f0[e] : zero;
+    const unsigned slot = lane * kCellsPerLane + b;
+    L.ok[b] = ((int)slot >= HALO) && (slot < (unsigned)(kWarpCells - HALO)) && (e >= 2u) && (e < a.m + 2u);
+  }
+
+  /* ---- phase A: this chunk's total ---- */
+  cx<F> tot[kCellsPerLane];
+#pragma unroll
+  for (int b = 0; b < kCellsPerLane; ++b)
+  {
+    tot[b] = zero;
+    L.ph[b] = start[b];
+  }
+  {
+    const unsigned body = cs.len - 1;
+#pragma unroll 2
+    for (unsigned i = 0; i < body; ++i)
+    {
+      const F d = sdelta[i];
+#pragma unroll
+      for (int b = 0; b < kCellsPerLane; ++b)
+      {
+        tot[b] = Arith<F>::mac(tot[b], L.ph[b], d);
+        L.ph[b] = Arith<F>::rotate(L.ph[b], L.tw[b]);
+      }
+    }
+    const F d = sdelta[body];
+#pragma unroll
+    for (int b = 0; b < kCellsPerLane; ++b) tot[b] = Arith<F>::mac(tot[b], L.ph[b], d);
+  }
+  if (last_chunk)
+  {
+    /* phase the next call starts with (sdft.h:573 / :584) */
+    cx<F>* po = a.phase_out + (size_t)ch * a.cells;
+#pragma unroll
+    for (int b = 0; b < kCellsPerLane; ++b)
+      if (live[b]) po[e0 + b] = cs.wraps ? restart[b] : Arith<F>::rotate(L.ph[b], L.tw[b]);
+  }
+
+  /* ---- carry: decoupled look-back with a deterministic, left-to-right summation ----
+   * Every item first publishes its own total ("aggregate"), which depends on nothing.  To obtain its
+   * carry an item walks back over its predecessors' flags, 32 at a time, to the nearest one whose
+   * inclusive PREFIX is already known, then adds prefix[q] + total[q+1] + ... + total[j-1] from left
+   * to right.  That is the very sequence of additions the serial chain would perform, so the result
+   * is bit-identical whatever q happens to be, but no item ever waits for a chain of predecessors. */
+  const size_t item = ((size_t)ch * a.sched.nchunks + j) * a.groups + group;
+  const size_t item_stride = a.groups;                      // distance between consecutive chunks
+  const unsigned code_total = a.epoch * 2u, code_prefix = a.epoch * 2u + 1u;
+  if (j == 0)
+  {
+    const cx<F>* ai = a.acc_in + (size_t)ch * a.cells;
+#pragma unroll
+    for (int b = 0; b < kCellsPerLane; ++b) L.acc[b] = live[b] ? ai[e0 + b] : zero;
+  }
+  else
+  {
+    if (!last_chunk)
+    {
+      cx<F>* tp = a.totals + item * kWarpCells + lane * kCellsPerLane;
+#pragma unroll
+      for (int b = 0; b < kCellsPerLane; ++b) store_l2<F>(tp + b, tot[b]);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release_u32(a.flags + item, code_total);
+    }
+    /* find q = nearest predecessor with a published prefix; all items in (q, j) must have totals */
+    long long top = (long long)j - 1;
+    long long q = -1;
+    unsigned long long t_start = 0;
+    while (true)
+    {
+      const long long idx = top - (long long)lane;
+      unsigned f = 0;
+      if (idx >= 0) f = ld_acquire_u32(a.flags + (item - (size_t)(j - idx) * item_stride));
+      const bool is_prefix = (idx >= 0) && (f == code_prefix);
+      const bool is_none = (idx >= 0) && (f != code_prefix) && (f != code_total);
+      const unsigned mask_prefix = __ballot_sync(0xffffffffu, is_prefix);
+      const unsigned mask_none = __ballot_sync(0xffffffffu, is_none);
+      if (mask_prefix)
+      {
+        const int first = __ffs(mask_prefix) - 1;
+        if ((mask_none & ((1u << first) - 1u)) == 0u)
+        {
+          q = top - first;
+          break;
+        }
+      }
+      else if (mask_none == 0u)
+      {
+        top -= 32;      // 32 totals and no prefix yet: look further back
+        continue;
+      }
+      /* a predecessor in the window has published nothing yet: wait for it */
+      __nanosleep(40);
+      if (t_start == 0) t_start = global_timer_ns();
+      else if (global_timer_ns() - t_start > kSpinLimitNs)
+      {
+        if (lane == 0) atomicExch(&a.control[1], 1u);
+        q = 0;
+        break;
+      }
+    }
+    __threadfence();
+    {
+      const size_t qi = item - (size_t)(j - q) * item_stride;
+      const cx<F>* pp = a.prefix + qi * kWarpCells + lane * kCellsPerLane;
+#pragma unroll
+      for (int b = 0; b < kCellsPerLane; ++b) L.acc[b] = load_l2<F>(pp + b);
+      for (long long r = q + 1; r < (long long)j; ++r)
+      {
+        const size_t ri = item - (size_t)(j - r) * item_stride;
+        const cx<F>* tp = a.totals + ri * kWarpCells + lane * kCellsPerLane;
+        cx<F> v[kCellsPerLane];
+#pragma unroll
+        for (int b = 0; b < kCellsPerLane; ++b) v[b] = load_l2<F>(tp + b);
+#pragma unroll
+        for (int b = 0; b < kCellsPerLane; ++b)
+        {
+          L.acc[b].r = Arith<F>::add(L.acc[b].r, v[b].r);
+          L.acc[b].i = Arith<F>::add(L.acc[b].i, v[b].i);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < kCellsPerLane; ++b)
+  {
+    tot[b].r = Arith<F>::add(L.acc[b].r, tot[b].r);
+    tot[b].i = Arith<F>::add(L.acc[b].i, tot[b].i);
+  }
+  if (!last_chunk)
+  {
+    cx<F>* pp = a.prefix + item * kWarpCells + lane * kCellsPerLane;
+#pragma unroll
+    for (int b = 0; b < kCellsPerLane; ++b) store_l2<F>(pp + b, tot[b]);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release_u32(a.flags + item, code_prefix);
+  }
+  else
+  {
+    /* accumulators the next call starts with (sdft.h:157) */
+    cx<F>* ao = a.acc_out + (size_t)ch * a.cells;
+#pragma unroll
+    for (int b = 0; b < kCellsPerLane; ++b)
+      if (live[b]) ao[e0 + b] = tot[b];
+  }
+
+  /* ---- phase B: replay from the carry and stream the rows out ---- */
+  if (EMIT)
+  {
+#pragma unroll
+    for (int b = 0; b < kCellsPerLane; ++b) L.ph[b] = start[b];
+    const size_t row_stride = a.m;
+    L.dst = a.out + (size_t)ch * a.out_channel_stride + (size_t)cs.t0 * row_stride + ((long long)e0 - 2);
+    const unsigned body = cs.wraps ? cs.len - 1 : cs.len;
+#pragma unroll 2
+    for (unsigned i = 0; i < body; ++i)
+    {
+      L.template step<false>(sdelta[i], restart, a.win, row_stride);
+    }
+    if (cs.wraps)
+    {
+      L.template step<true>(sdelta[body], restart, a.win, row_stride);
+    }
   }
 }
 
