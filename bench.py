@@ -85,12 +85,12 @@ class ClockSampler:
             self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=self.file, stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=self.file, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "power_w": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
         try:
@@ -104,17 +104,17 @@ class ClockSampler:
             os.unlink(self.file.name)
         except Exception:
             rows = []
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
                 for name, v in zip(self.NAMES, r[3:7]):
                     if "Active" in v and "Not" not in v:
                         reasons.add(name)
             except Exception:
                 continue
         if sm:
-            out.update({"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+            out.update({"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w": float(np.median(pw)), "reasons": sorted(reasons),
                         "samples": len(sm)})
         return out
 
@@ -275,7 +275,7 @@ def run_b200_arm(args, rank, local_rank, world):
             traffic = tj["dram_bytes_per_bin_update"] * n * m
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "emit_kernel<double>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "scan_emit_kernel<double> (chunk totals + look-back + row stores, one launch per call)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dur * 1e3, "launches_timed": kcount,
                 "whole_call_GBps": args.steps * 4 * alg_bytes / t_analysis / 1e9}
@@ -323,6 +323,32 @@ def run_b200_arm(args, rank, local_rank, world):
                      "PCIe-bound: %.1f GB/s device->host" % (n_e, m, args.steps * n_e * m * 16 / t_e2e / 1e9)}
     launches += pe.launches - e2e_launch0
     del oe
+
+    # the reference's own usage pattern (test/test.c:79-80): analysis then synthesis, hop by hop, with only
+    # SAMPLES crossing PCIe (host in, host out) and the rows living in a device tile
+    n_rt = min(1 << 18, n)
+    xr = torch.from_numpy(x_host[:n_rt].copy()).pin_memory()
+    yr = torch.empty(n_rt, dtype=torch.float32).pin_memory()
+    pr = SDFT(m, "hann", 1, td="f32", fd="f64")
+    xrp, yrp = ctypes.c_void_p(xr.data_ptr()), ctypes.c_void_p(yr.data_ptr())
+    for _ in range(2):
+        pr._f("roundtrip_n")(pr._h, n_rt, xrp, yrp)
+    pr._check()
+    rt_launch0 = pr.launches
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pr._f("roundtrip_n")(pr._h, n_rt, xrp, yrp)
+    torch.cuda.synchronize()
+    t_rt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    pr._check()
+    launches += pr.launches - rt_launch0
+    e2e["roundtrip"] = {"value": world * args.steps * n_rt * m / t_rt, "unit": UNIT,
+                        "samples_per_s": world * args.steps * n_rt / t_rt,
+                        "h2d_bytes_per_step": n_rt * 4, "d2h_bytes_per_step": n_rt * 4,
+                        "sample": "sdft_b200_f32f64_roundtrip_n(host samples -> host samples), n=%d, m=%d, hann: "
+                                  "analysis + synthesis, rows stay in a device tile" % (n_rt, m)}
 
     # ---- CPU baseline beside it (rank 0, N = 1) -----------------------------------------------------
     cpu = None

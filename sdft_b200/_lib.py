@@ -68,7 +68,7 @@ def load(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("SDFT_B200_LIB") or LIB_PATH
     if not os.path.exists(path):
         from . import build as _build
         _build.build()

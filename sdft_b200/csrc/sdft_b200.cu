@@ -4,8 +4,9 @@
  *
  * What lives where (reference: struct sdft_plan, c/src/sdft/sdft.h:137-182):
  *   tables   tw_ext[m+4], tws[m], F0[ceil(2m/32)][m+4]         device, written once per plan
- *   state    history[2][2m] and phase_state[2][m+4] (ping-pong), acc_state[m+4] per channel; cursor on the host
- *   scratch  samples, deltas, chunk totals/carries, row tiles   device, grow-only
+ *   state    history[2][2m] and acc_state[2][m+4] (ping-pong) per channel; the cursor lives on the host and the
+ *            modulation phase is a pure function of it (table row + <32 rotations), so it is not stored
+ *   scratch  samples, deltas, chunk totals/prefixes/flags of the chained scan, row tiles   device, grow-only
  *
  * No CPU fallback: every entry point either runs the CUDA path or records an error on the plan.
  */
@@ -26,6 +27,15 @@ using namespace sdftb200;
  * plan
  * ---------------------------------------------------------------------------------------------- */
 enum TypeId { kF32 = 0, kF64 = 1 };
+
+/* mirror cells (sdft.h:589-595): source bin (or -1 = always zero) and whether the copy is conjugated;
+ * only used on the host to lay out the extended twiddle table */
+struct MirrorMap
+{
+  int cell[4];
+  int src[4];
+  int conj[4];
+};
 
 struct Buffer
 {
@@ -55,6 +65,8 @@ struct sdft_b200_plan
   unsigned long long launches = 0;
 
   MirrorMap mirrors;
+  int mode = 0;                  // MODE_MODULATED / MODE_FAST (double frequency domain only)
+  double prescale = 1.0;         // factor folded into the deltas in fast mode (acc_state is scaled by it)
   void* tw_ext = nullptr;
   void* tws = nullptr;
   void* f0 = nullptr;
@@ -64,14 +76,12 @@ struct sdft_b200_plan
   int hist_sel = 0;
   void* acc_state[2] = { nullptr, nullptr };     // ping-pong, same reason (neighbouring groups share halo cells)
   int acc_sel = 0;
-  void* phase_state[2] = { nullptr, nullptr };   // ping-pong: emit still reads the phase the call started with
-  int phase_sel = 0;
+  void* phase_scratch = nullptr;   // cells complex values, introspection only
 
-  Buffer samples, deltas, totals, synth_out, tile[2];
+  Buffer samples, deltas, synth_out, tile[2];
   Buffer prefix, chain_totals, flags;   // chained scan: inclusive prefixes, chunk totals, epoch-stamped flags
   unsigned* control = nullptr;   // [0] work ticket, [1] spin-wait timeout flag
   unsigned epoch = 0;
-  bool three_pass = false;       // SDFT_B200_PIPELINE=3pass: separate totals / carry / emit kernels
 
   /* optional CUDA-event timing of the dominant kernels (bench.py roofline): [0] analysis emit, [1] synthesis */
   bool profiling = false;
@@ -277,16 +287,15 @@ bool plan_build(Plan* p)
   CU_TRY(p, cudaMalloc(&p->acc_state[1], ch * cells * sizeof(cx<F>)));
   CU_TRY(p, cudaMalloc(&p->control, 2 * sizeof(unsigned)));
   CU_TRY(p, cudaMemsetAsync(p->control, 0, 2 * sizeof(unsigned), p->stream));
-  CU_TRY(p, cudaMalloc(&p->phase_state[0], ch * cells * sizeof(cx<F>)));
-  CU_TRY(p, cudaMalloc(&p->phase_state[1], ch * cells * sizeof(cx<F>)));
+  CU_TRY(p, cudaMalloc(&p->phase_scratch, cells * sizeof(cx<F>)));
 
   CU_TRY(p, cudaMemcpyAsync(p->tw_ext, tw_ext.data(), cells * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
   CU_TRY(p, cudaMemcpyAsync(p->tws, tws.data(), m * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
-  /* stage P0 in phase_state[channel 0], expand it into the table, then reset copies row 0 everywhere */
-  CU_TRY(p, cudaMemcpyAsync(p->phase_state[0], p0.data(), cells * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
+  /* stage P0 (1, or 0 for always-zero mirror cells), expand it into the table */
+  CU_TRY(p, cudaMemcpyAsync(p->phase_scratch, p0.data(), cells * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
   const unsigned threads = 128;
   phase_table_kernel<F><<<(unsigned)((cells + threads - 1) / threads), threads, 0, p->stream>>>(
-      (const cx<F>*)p->tw_ext, (const cx<F>*)p->phase_state[0], (cx<F>*)p->f0, (unsigned)cells, (unsigned)(2 * m));
+      (const cx<F>*)p->tw_ext, (const cx<F>*)p->phase_scratch, (cx<F>*)p->f0, (unsigned)cells, (unsigned)(2 * m));
   p->launches++;
   CU_TRY(p, cudaGetLastError());
   CU_TRY(p, cudaStreamSynchronize(p->stream));   // host vectors go out of scope
@@ -299,16 +308,10 @@ bool plan_reset(Plan* p)
   const size_t m = p->m, cells = p->cells, ch = p->channels;
   p->cursor = 0;
   p->hist_sel = 0;
-  p->phase_sel = 0;
   p->acc_sel = 0;
   CU_TRY(p, cudaMemsetAsync(p->history[0], 0, ch * 2 * m * sizeof(T), p->stream));
   CU_TRY(p, cudaMemsetAsync(p->acc_state[0], 0, ch * cells * sizeof(cx<F>), p->stream));
   CU_TRY(p, cudaMemsetAsync(p->acc_state[1], 0, ch * cells * sizeof(cx<F>), p->stream));
-  for (size_t c = 0; c < ch; ++c)
-  {
-    CU_TRY(p, cudaMemcpyAsync((cx<F>*)p->phase_state[0] + c * cells, p->f0, cells * sizeof(cx<F>),
-                              cudaMemcpyDeviceToDevice, p->stream));
-  }
   return true;
 }
 
@@ -318,9 +321,9 @@ void plan_destroy(Plan* p)
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
-  void* ptrs[] = { p->tw_ext, p->tws, p->f0, p->history[0], p->history[1], p->acc_state[0], p->acc_state[1], p->phase_state[0], p->phase_state[1],
+  void* ptrs[] = { p->tw_ext, p->tws, p->f0, p->history[0], p->history[1], p->acc_state[0], p->acc_state[1], p->phase_scratch,
                    p->prefix.ptr, p->chain_totals.ptr, p->flags.ptr, p->control,
-                   p->samples.ptr, p->deltas.ptr, p->totals.ptr, p->synth_out.ptr, p->tile[0].ptr, p->tile[1].ptr };
+                   p->samples.ptr, p->deltas.ptr, p->synth_out.ptr, p->tile[0].ptr, p->tile[1].ptr };
   for (void* q : ptrs)
     if (q) cudaFree(q);
   for (int w = 0; w < 2; ++w)
@@ -366,8 +369,12 @@ Plan* plan_create(size_t m, int window, double latency, size_t channels)
   p->tile_bytes = env_size("SDFT_B200_TILE_MB", 128) << 20;
   p->forced_chunk = env_size("SDFT_B200_CHUNK", 0);
   {
-    const char* pl = getenv("SDFT_B200_PIPELINE");
-    p->three_pass = pl && !strcmp(pl, "3pass");
+    /* double frequency domain: fast (demodulated replay) unless SDFT_B200_F64=modulated; float always
+     * follows the reference's modulated scheme operation by operation */
+    const char* md = getenv("SDFT_B200_F64");
+    const bool modulated = md && !strcmp(md, "modulated");
+    p->mode = (type_id<F>::value == kF64 && !modulated) ? MODE_FAST : MODE_MODULATED;
+    p->prescale = (p->mode == MODE_FAST) ? (double)make_window_const<double>(m, window).pre : 1.0;
   }
 
   bool ok = true;
@@ -414,8 +421,18 @@ void prof_mark(Plan* p, int which)
 
 unsigned groups_for(const Plan* p)
 {
-  const unsigned span = (p->window == 0) ? kWarpCells : kWarpCells - 4;
+  const unsigned wc = (p->fd == kF32) ? (unsigned)Geo<float>::WC : (unsigned)Geo<double>::WC;
+  const unsigned halo = (p->window == 0) ? 0u : ((p->fd == kF32) ? (unsigned)Geo<float>::GROUP : (unsigned)Geo<double>::GROUP);
+  const unsigned span = wc - 2 * halo;
   return (unsigned)((p->m + span - 1) / span);
+}
+
+/* 32-byte group stores need rows that start on a 32-byte boundary */
+template <typename F>
+bool can_vectorize(size_t m, const void* out, size_t out_stride)
+{
+  const size_t g = Geo<F>::GROUP;
+  return (m % g == 0) && (((uintptr_t)out) % 32 == 0) && (out_stride % g == 0);
 }
 
 unsigned choose_chunk(const Plan* p, size_t n)
@@ -435,40 +452,39 @@ unsigned choose_chunk(const Plan* p, size_t n)
   return c;
 }
 
-template <typename F>
-void launch_emit(Plan* p, const EmitArgs<F>& a, dim3 grid, bool vec)
-{
-#define SDFT_EMIT_CASE(W)                                                                              \
-  case W:                                                                                              \
-    if (vec) emit_kernel<F, W, true><<<grid, kEmitWarps * 32, 0, p->stream>>>(a);                      \
-    else emit_kernel<F, W, false><<<grid, kEmitWarps * 32, 0, p->stream>>>(a);                         \
-    break;
-  switch (p->window)
-  {
-    SDFT_EMIT_CASE(0)
-    SDFT_EMIT_CASE(1)
-    SDFT_EMIT_CASE(2)
-    SDFT_EMIT_CASE(3)
-  }
-#undef SDFT_EMIT_CASE
-  p->launches++;
-}
-
 template <typename F, bool EMIT>
 void launch_chain(Plan* p, const ChainArgs<F>& a, bool vec)
 {
   const dim3 grid(a.total_blocks);
-#define SDFT_CHAIN_CASE(W)                                                                             \
+#define SDFT_CHAIN_CASE(W, MODE)                                                                       \
   case W:                                                                                              \
-    if (vec) scan_emit_kernel<F, W, true, EMIT><<<grid, kEmitWarps * 32, 0, p->stream>>>(a);           \
-    else scan_emit_kernel<F, W, false, EMIT><<<grid, kEmitWarps * 32, 0, p->stream>>>(a);              \
+    if (vec) scan_emit_kernel<F, W, true, EMIT, MODE><<<grid, kEmitWarps * 32, 0, p->stream>>>(a);     \
+    else scan_emit_kernel<F, W, false, EMIT, MODE><<<grid, kEmitWarps * 32, 0, p->stream>>>(a);        \
     break;
-  switch (p->window)
+  bool launched = false;
+  if constexpr (sizeof(F) == sizeof(double))
   {
-    SDFT_CHAIN_CASE(0)
-    SDFT_CHAIN_CASE(1)
-    SDFT_CHAIN_CASE(2)
-    SDFT_CHAIN_CASE(3)
+    if (p->mode == MODE_FAST)
+    {
+      launched = true;
+      switch (p->window)
+      {
+        SDFT_CHAIN_CASE(0, MODE_FAST)
+        SDFT_CHAIN_CASE(1, MODE_FAST)
+        SDFT_CHAIN_CASE(2, MODE_FAST)
+        SDFT_CHAIN_CASE(3, MODE_FAST)
+      }
+    }
+  }
+  if (!launched)
+  {
+    switch (p->window)
+    {
+      SDFT_CHAIN_CASE(0, MODE_MODULATED)
+      SDFT_CHAIN_CASE(1, MODE_MODULATED)
+      SDFT_CHAIN_CASE(2, MODE_MODULATED)
+      SDFT_CHAIN_CASE(3, MODE_MODULATED)
+    }
   }
 #undef SDFT_CHAIN_CASE
   p->launches++;
@@ -493,8 +509,8 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   }
 
   if (!reserve(p, p->deltas, (size_t)ch * n * sizeof(F))) return false;
-  if (!reserve(p, p->prefix, items * kWarpCells * sizeof(cx<F>))) return false;
-  if (!reserve(p, p->chain_totals, items * kWarpCells * sizeof(cx<F>))) return false;
+  if (!reserve(p, p->prefix, items * Geo<F>::WC * sizeof(cx<F>))) return false;
+  if (!reserve(p, p->chain_totals, items * Geo<F>::WC * sizeof(cx<F>))) return false;
   const size_t flags_before = p->flags.bytes;
   if (!reserve(p, p->flags, items * sizeof(unsigned))) return false;
   if (p->flags.bytes != flags_before || p->epoch >= 0x7ffffff0u)
@@ -510,7 +526,7 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
     if (kblocks > 2048) kblocks = 2048;
     delta_kernel<T, F><<<dim3(kblocks, ch), 256, 0, p->stream>>>(
         x, x_stride, (const T*)p->history[p->hist_sel], (T*)p->history[p->hist_sel ^ 1],
-        (F*)p->deltas.ptr, n, n, 2 * m);
+        (F*)p->deltas.ptr, n, n, 2 * m, (F)p->prescale);
     p->launches++;
     p->hist_sel ^= 1;
   }
@@ -521,8 +537,6 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   a.delta_stride = n;
   a.tw_ext = (const cx<F>*)p->tw_ext;
   a.f0 = (const cx<F>*)p->f0;
-  a.phase_in = (const cx<F>*)p->phase_state[p->phase_sel];
-  a.phase_out = (cx<F>*)p->phase_state[p->phase_sel ^ 1];
   a.acc_in = (const cx<F>*)p->acc_state[p->acc_sel];
   a.acc_out = (cx<F>*)p->acc_state[p->acc_sel ^ 1];
   a.prefix = (cx<F>*)p->prefix.ptr;
@@ -540,8 +554,7 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   a.win = make_window_const<F>(p->m, p->window);   // sdft.h:422, :371
   if (out)
   {
-    const size_t pair_bytes = 2 * sizeof(cx<F>);
-    const bool vec = (m % 2 == 0) && (((uintptr_t)out) % pair_bytes == 0) && (out_stride % 2 == 0);
+    const bool vec = can_vectorize<F>(m, out, out_stride);
     prof_mark(p, 0);
     launch_chain<F, true>(p, a, vec);
     prof_mark(p, 0);
@@ -552,7 +565,6 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   }
   CU_TRY(p, cudaGetLastError());
   p->cursor = (size_t)((p->cursor + n) % (2 * (size_t)m));
-  p->phase_sel ^= 1;
   p->acc_sel ^= 1;
   return true;
 }
@@ -563,69 +575,7 @@ template <typename T, typename F>
 bool analysis_device(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride)
 {
   if (n == 0) return true;
-  if (!p->three_pass) return analysis_chained<T, F>(p, n, x, x_stride, out, out_stride);
-  const unsigned m = (unsigned)p->m;
-  const unsigned ch = (unsigned)p->channels;
-  const unsigned chunk = choose_chunk(p, n);
-  const Schedule sched = make_schedule(p->cursor, n, m, chunk);
-
-  if (!reserve(p, p->deltas, (size_t)ch * n * sizeof(F))) return false;
-  if (!reserve(p, p->totals, (size_t)ch * sched.nchunks * p->cells * sizeof(cx<F>))) return false;
-
-  /* K1 */
-  {
-    const size_t work = n > 2 * (size_t)m ? n : 2 * (size_t)m;
-    unsigned blocks = (unsigned)((work + 255) / 256);
-    if (blocks > 2048) blocks = 2048;
-    delta_kernel<T, F><<<dim3(blocks, ch), 256, 0, p->stream>>>(
-        x, x_stride, (const T*)p->history[p->hist_sel], (T*)p->history[p->hist_sel ^ 1],
-        (F*)p->deltas.ptr, n, n, 2 * m);
-    p->launches++;
-    p->hist_sel ^= 1;
-  }
-
-  ScanArgs<F> s;
-  s.sched = sched;
-  s.delta = (const F*)p->deltas.ptr;
-  s.delta_stride = n;
-  s.tw_ext = (const cx<F>*)p->tw_ext;
-  s.f0 = (const cx<F>*)p->f0;
-  s.phase_in = (const cx<F>*)p->phase_state[p->phase_sel];
-  s.phase_out = (cx<F>*)p->phase_state[p->phase_sel ^ 1];
-  s.acc_state = (cx<F>*)p->acc_state[p->acc_sel];
-  s.totals = (cx<F>*)p->totals.ptr;
-  s.m = m;
-  s.cells = (unsigned)p->cells;
-  s.mirrors = p->mirrors;
-
-  /* K2, K2b */
-  {
-    const unsigned bin_blocks = (m + kTotalsThreads - 1) / kTotalsThreads;
-    chunk_totals_kernel<F><<<dim3(sched.nchunks * bin_blocks, ch), kTotalsThreads, 0, p->stream>>>(s);
-    carry_scan_kernel<F><<<dim3(bin_blocks, ch), kTotalsThreads, 0, p->stream>>>(s);
-    p->launches += 2;
-  }
-
-  /* K3 */
-  if (out)
-  {
-    EmitArgs<F> a;
-    a.scan = s;
-    a.out = out;
-    a.out_channel_stride = out_stride;
-    a.groups = groups_for(p);
-    a.group_blocks = (a.groups + kEmitWarps - 1) / kEmitWarps;
-    a.win = make_window_const<F>(p->m, p->window);   // sdft.h:422, :371
-    const size_t pair_bytes = 2 * sizeof(cx<F>);
-    const bool vec = (m % 2 == 0) && (((uintptr_t)out) % pair_bytes == 0) && (out_stride % 2 == 0);
-    prof_mark(p, 0);
-    launch_emit<F>(p, a, dim3(sched.nchunks * a.group_blocks, ch), vec);
-    prof_mark(p, 0);
-  }
-  CU_TRY(p, cudaGetLastError());
-  p->cursor = (size_t)((p->cursor + n) % (2 * (size_t)m));
-  p->phase_sel ^= 1;
-  return true;
+  return analysis_chained<T, F>(p, n, x, x_stride, out, out_stride);
 }
 
 template <typename T, typename F>
@@ -1078,11 +1028,30 @@ extern "C" int sdft_b200_get_state(sdft_b200_plan_t* p, size_t channel, size_t* 
     e = cudaMemcpy(history, (char*)p->history[p->hist_sel] + channel * 2 * p->m * tbytes, 2 * p->m * tbytes,
                    cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && accumulators)
+  {
     e = cudaMemcpy(accumulators, (char*)p->acc_state[p->acc_sel] + (channel * p->cells + 2) * cbytes, p->m * cbytes,
                    cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && p->prescale != 1.0)
+    {
+      /* fast mode keeps the accumulators multiplied by the folded window factor */
+      double* a = (double*)accumulators;
+      for (size_t i = 0; i < 2 * p->m; ++i) a[i] /= p->prescale;
+    }
+  }
   if (e == cudaSuccess && phase)
-    e = cudaMemcpy(phase, (char*)p->phase_state[p->phase_sel] + (channel * p->cells + 2) * cbytes, p->m * cbytes,
-                   cudaMemcpyDeviceToHost);
+  {
+    const unsigned threads = 128, blocks = (unsigned)((p->cells + threads - 1) / threads);
+    if (p->fd == kF32)
+      phase_at_kernel<float><<<blocks, threads, 0, p->stream>>>((const cx<float>*)p->tw_ext, (const cx<float>*)p->f0,
+                                                                (cx<float>*)p->phase_scratch, (unsigned)p->cells, (unsigned)p->cursor);
+    else
+      phase_at_kernel<double><<<blocks, threads, 0, p->stream>>>((const cx<double>*)p->tw_ext, (const cx<double>*)p->f0,
+                                                                 (cx<double>*)p->phase_scratch, (unsigned)p->cells, (unsigned)p->cursor);
+    p->launches++;
+    e = cudaStreamSynchronize(p->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(phase, (char*)p->phase_scratch + 2 * cbytes, p->m * cbytes, cudaMemcpyDeviceToHost);
+  }
   if (e != cudaSuccess) plan_fail(p, (int)e, "sdft_b200_get_state", __FILE__, __LINE__);
   return p->status;
 }

@@ -16,9 +16,18 @@
  *                    2m period nor the period end; every chunk but the first of a call therefore
  *                    starts at a cursor that is a multiple of L and reads its phase from the F0 table
  *
- * Arithmetic policy: float frequency-domain data reproduces the reference's
- * rounding points with un-fused _rn intrinsics; double uses explicit FMAs in a FIXED pattern so that
- * every kernel generates bit-identical phases (the telescoping of x[t] - x[t-2m] depends on it).
+ * Arithmetic policy
+ *   float   reproduces every rounding point of the reference (un-fused, packed FMUL2/FADD2): phases
+ *           are bit-exact and rows are bit-exact within a chunk; only the summation order across
+ *           chunks differs.
+ *   double  MODE_MODULATED: the reference's scheme with explicit FMAs in a fixed pattern.
+ *           MODE_FAST (default): the chunk total is a Horner sum of tw^i * delta_i scaled by the phase
+ *           at the chunk start, and the replay runs the demodulated recurrence
+ *           aux <- (aux + delta) * conj(tw) anchored at carry * conj(P_start) at every chunk start,
+ *           with the window weight folded into the deltas.  13 instead of 22 FP64 instructions per
+ *           bin-update (Hann); the B200 is power-capped on this path, so fewer FP64 operations is
+ *           more bandwidth.  Mathematically identical, differs by rounding (~1e-12 of full scale,
+ *           gate is 1e-9); the phase still restarts exactly every 2m samples.
  */
 #pragma once
 
@@ -32,55 +41,182 @@ constexpr int kF0Stride = 32;     // phase table holds P at every 32nd cursor
 constexpr int kMaxChunk = 1024;   // longest chunk the kernels accept (samples)
 constexpr int kAutoChunk = 512;   // longest chunk the heuristic picks (measured best on B200)
 constexpr int kEmitWarps = 4;     // warps per emit CTA
-constexpr int kCellsPerLane = 4;  // consecutive cells owned by one lane
-constexpr int kWarpCells = 32 * kCellsPerLane;
 
 template <typename F> struct cx { F r, i; };
 
+/* Work geometry of the emit warps.  A lane owns CPL consecutive cells and stores them as 32-byte
+ * groups of GROUP cells; the halo on either side of a warp is one group wide (>= the 2 cells the
+ * Blackman taps need), which keeps every group store 32-byte aligned. */
+template <typename F> struct Geo;
+template <> struct Geo<double> { enum { CPL = 4, GROUP = 2, WC = 32 * 4 }; };
+template <> struct Geo<float>  { enum { CPL = 8, GROUP = 4, WC = 32 * 8 }; };
+
 /* ------------------------------------------------------------------------------------------------
- * arithmetic policies
+ * arithmetic policies (complex level)
  * ---------------------------------------------------------------------------------------------- */
+template <typename F> struct WindowConst
+{
+  F w;       // analysis weight 1/(2m)                        sdft.h:422
+  F wq;      // w * 0.25, the Hann factor                     sdft.h:371
+  F c0, c1, c2;   // double, modulated mode: weight folded into centre / first / second neighbour taps
+  F pre;          // double, fast mode: factor folded into the deltas (whole weight times one tap)
+  F k0, k1;       // double, fast mode: remaining tap ratios
+};
+
+template <typename F>
+inline WindowConst<F> make_window_const(size_t m, int window)
+{
+  WindowConst<F> k;
+  k.w = (F)(1) / (F)(m * 2);
+  k.wq = k.w * (F)(0.25);
+  switch (window)
+  {
+    case 1: k.c0 = (F)2 * k.wq; k.c1 = k.wq; k.c2 = (F)0; break;
+    case 2: k.c0 = (F)(0.54) * k.w; k.c1 = (F)(0.23) * k.w; k.c2 = (F)0; break;
+    case 3: k.c0 = (F)(0.42) * k.w; k.c1 = (F)(0.25) * k.w; k.c2 = (F)(0.04) * k.w; break;
+    default: k.c0 = k.w; k.c1 = (F)0; k.c2 = (F)0; break;
+  }
+  /* fast mode, taps on pre-scaled data: hann 2c-(l+r); hamming k0*c-(l+r);
+   * blackman (l2+r2) + k0*c - k1*(l1+r1); boxcar c */
+  switch (window)
+  {
+    case 1: k.pre = k.wq; k.k0 = (F)2; k.k1 = (F)0; break;
+    case 2: k.pre = (F)(0.23) * k.w; k.k0 = (F)(0.54) / (F)(0.23); k.k1 = (F)0; break;
+    case 3: k.pre = (F)(0.04) * k.w; k.k0 = (F)(0.42) / (F)(0.04); k.k1 = (F)(0.25) / (F)(0.04); break;
+    default: k.pre = k.w; k.k0 = (F)1; k.k1 = (F)0; break;
+  }
+  return k;
+}
+
 template <typename F> struct Arith;
+
+/* float: every operation of the reference is kept as its own rounding step (bit-exact phases and,
+ * within a chunk, bit-exact rows).  Products use the packed FMUL2/FADD2 forms of sm_100a on the
+ * (re, im) register pair to halve the issue slots.  ptxas contracts a packed mul.rn.f32x2 feeding a
+ * packed add/sub.rn.f32x2 into FFMA2 (observed with CUDA 12.9, even with --fmad=false), so every
+ * addition that consumes a product is a SCALAR add.rn/sub.rn, which ptxas never fuses. */
+__device__ __forceinline__ cx<float> pk_mul(cx<float> a, cx<float> b)        // (a.r*b.r, a.i*b.i)
+{
+  cx<float> o;
+  asm("{.reg .b64 x, y, z; mov.b64 x, {%2, %3}; mov.b64 y, {%4, %5}; mul.rn.f32x2 z, x, y; mov.b64 {%0, %1}, z;}"
+      : "=f"(o.r), "=f"(o.i) : "f"(a.r), "f"(a.i), "f"(b.r), "f"(b.i));
+  return o;
+}
+__device__ __forceinline__ cx<float> pk_mul_cross(cx<float> a, cx<float> b)  // (a.r*b.i, a.i*b.r)
+{
+  cx<float> o;
+  asm("{.reg .b64 x, y, z; mov.b64 x, {%2, %3}; mov.b64 y, {%5, %4}; mul.rn.f32x2 z, x, y; mov.b64 {%0, %1}, z;}"
+      : "=f"(o.r), "=f"(o.i) : "f"(a.r), "f"(a.i), "f"(b.r), "f"(b.i));
+  return o;
+}
+__device__ __forceinline__ cx<float> pk_scale(cx<float> a, float k)          // (a.r*k, a.i*k)
+{
+  cx<float> o;
+  asm("{.reg .b64 x, y, z; mov.b64 x, {%2, %3}; mov.b64 y, {%4, %4}; mul.rn.f32x2 z, x, y; mov.b64 {%0, %1}, z;}"
+      : "=f"(o.r), "=f"(o.i) : "f"(a.r), "f"(a.i), "f"(k));
+  return o;
+}
+__device__ __forceinline__ cx<float> pk_add(cx<float> a, cx<float> b)
+{
+  cx<float> o;
+  asm("{.reg .b64 x, y, z; mov.b64 x, {%2, %3}; mov.b64 y, {%4, %5}; add.rn.f32x2 z, x, y; mov.b64 {%0, %1}, z;}"
+      : "=f"(o.r), "=f"(o.i) : "f"(a.r), "f"(a.i), "f"(b.r), "f"(b.i));
+  return o;
+}
+__device__ __forceinline__ cx<float> pk_sub(cx<float> a, cx<float> b)
+{
+  cx<float> o;
+  asm("{.reg .b64 x, y, z; mov.b64 x, {%2, %3}; mov.b64 y, {%4, %5}; sub.rn.f32x2 z, x, y; mov.b64 {%0, %1}, z;}"
+      : "=f"(o.r), "=f"(o.i) : "f"(a.r), "f"(a.i), "f"(b.r), "f"(b.i));
+  return o;
+}
 
 template <> struct Arith<float>
 {
   typedef float F;
-  static __device__ __forceinline__ F add(F a, F b) { return __fadd_rn(a, b); }
-  static __device__ __forceinline__ F sub(F a, F b) { return __fsub_rn(a, b); }
-  static __device__ __forceinline__ F mul(F a, F b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ cx<F> cadd(cx<F> a, cx<F> b)
+  {
+    cx<F> o;
+    o.r = __fadd_rn(a.r, b.r);
+    o.i = __fadd_rn(a.i, b.i);
+    return o;
+  }
   /* P * tw, sdft.h:584 via :298-300 -- bit-exact with the reference */
   static __device__ __forceinline__ cx<F> rotate(cx<F> p, cx<F> w)
   {
+    const cx<F> t1 = pk_mul(p, w);         // (pr*wr, pi*wi)
+    const cx<F> t2 = pk_mul_cross(p, w);   // (pr*wi, pi*wr)
     cx<F> o;
-    o.r = __fsub_rn(__fmul_rn(p.r, w.r), __fmul_rn(p.i, w.i));
-    o.i = __fadd_rn(__fmul_rn(p.r, w.i), __fmul_rn(p.i, w.r));
+    o.r = __fsub_rn(t1.r, t1.i);
+    o.i = __fadd_rn(t2.r, t2.i);
     return o;
   }
   /* acc + P * delta, sdft.h:583 */
   static __device__ __forceinline__ cx<F> mac(cx<F> acc, cx<F> p, F d)
   {
+    const cx<F> t = pk_scale(p, d);
     cx<F> o;
-    o.r = __fadd_rn(acc.r, __fmul_rn(p.r, d));
-    o.i = __fadd_rn(acc.i, __fmul_rn(p.i, d));
+    o.r = __fadd_rn(acc.r, t.r);
+    o.i = __fadd_rn(acc.i, t.i);
     return o;
   }
-  /* acc * conj(P), sdft.h:585 */
+  /* acc * conj(P), sdft.h:585: (ar*pr - ai*(-pi), ar*(-pi) + ai*pr) */
   static __device__ __forceinline__ cx<F> demod(cx<F> a, cx<F> p)
   {
-    const F ci = -p.i;
+    const cx<F> t1 = pk_mul(a, p);         // (ar*pr, ai*pi)
+    const cx<F> t2 = pk_mul_cross(a, p);   // (ar*pi, ai*pr)
     cx<F> o;
-    o.r = __fsub_rn(__fmul_rn(a.r, p.r), __fmul_rn(a.i, ci));
-    o.i = __fadd_rn(__fmul_rn(a.r, ci), __fmul_rn(a.i, p.r));
+    o.r = __fadd_rn(t1.r, t1.i);
+    o.i = __fsub_rn(t2.i, t2.r);
     return o;
+  }
+  /* window taps in the reference's operation order, sdft.h:350-402 */
+  template <int WINDOW>
+  static __device__ __forceinline__ cx<F> window(cx<F> l2, cx<F> l1, cx<F> c, cx<F> r1, cx<F> r2, const WindowConst<F>& k)
+  {
+    if (WINDOW == 1)
+    {
+      return pk_scale(pk_sub(pk_add(c, c), pk_add(l1, r1)), k.wq);
+    }
+    else if (WINDOW == 2)
+    {
+      const cx<F> a = pk_scale(c, (F)(0.54));
+      const cx<F> b = pk_scale(pk_add(l1, r1), (F)(0.23));
+      cx<F> d;
+      d.r = __fsub_rn(a.r, b.r);
+      d.i = __fsub_rn(a.i, b.i);
+      return pk_scale(d, k.w);
+    }
+    else if (WINDOW == 3)
+    {
+      const cx<F> a = pk_scale(c, (F)(0.42));
+      const cx<F> b = pk_scale(pk_add(l1, r1), (F)(0.25));
+      const cx<F> e = pk_scale(pk_add(l2, r2), (F)(0.04));
+      cx<F> d;
+      d.r = __fadd_rn(__fsub_rn(a.r, b.r), e.r);
+      d.i = __fadd_rn(__fsub_rn(a.i, b.i), e.i);
+      return pk_scale(d, k.w);
+    }
+    else
+    {
+      return pk_scale(c, k.w);
+    }
   }
 };
 
+/* double: explicit FMAs in a FIXED pattern (every kernel generates bit-identical phases); the window
+ * weight is folded into the tap coefficients (3 / 3 / 5 FP64 instructions per component instead of
+ * 4 / 5 / 8).  Differs from the reference's operation order by rounding only (~1e-16). */
 template <> struct Arith<double>
 {
   typedef double F;
-  static __device__ __forceinline__ F add(F a, F b) { return __dadd_rn(a, b); }
-  static __device__ __forceinline__ F sub(F a, F b) { return __dsub_rn(a, b); }
-  static __device__ __forceinline__ F mul(F a, F b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ cx<F> cadd(cx<F> a, cx<F> b)
+  {
+    cx<F> o;
+    o.r = __dadd_rn(a.r, b.r);
+    o.i = __dadd_rn(a.i, b.i);
+    return o;
+  }
   static __device__ __forceinline__ cx<F> rotate(cx<F> p, cx<F> w)
   {
     cx<F> o;
@@ -102,79 +238,73 @@ template <> struct Arith<double>
     o.i = __fma_rn(a.i, p.r, -__dmul_rn(a.r, p.i));
     return o;
   }
+  template <int WINDOW>
+  static __device__ __forceinline__ F tap(F l2, F l1, F c, F r1, F r2, const WindowConst<F>& k)
+  {
+    if (WINDOW == 0)
+    {
+      return __dmul_rn(c, k.c0);
+    }
+    else if (WINDOW == 3)
+    {
+      const F t = __fma_rn(c, k.c0, -__dmul_rn(__dadd_rn(l1, r1), k.c1));
+      return __fma_rn(__dadd_rn(l2, r2), k.c2, t);
+    }
+    else
+    {
+      return __fma_rn(c, k.c0, -__dmul_rn(__dadd_rn(l1, r1), k.c1));
+    }
+  }
+  template <int WINDOW>
+  static __device__ __forceinline__ cx<F> window(cx<F> l2, cx<F> l1, cx<F> c, cx<F> r1, cx<F> r2, const WindowConst<F>& k)
+  {
+    cx<F> o;
+    o.r = tap<WINDOW>(l2.r, l1.r, c.r, r1.r, r2.r, k);
+    o.i = tap<WINDOW>(l2.i, l1.i, c.i, r1.i, r2.i, k);
+    return o;
+  }
+
+  /* ---- fast mode ---- */
+  /* Horner step of the chunk total: h <- h * tw + delta */
+  static __device__ __forceinline__ cx<F> horner(cx<F> h, cx<F> w, F d)
+  {
+    cx<F> o;
+    o.r = __fma_rn(h.r, w.r, __fma_rn(-h.i, w.i, d));
+    o.i = __fma_rn(h.r, w.i, __dmul_rn(h.i, w.r));
+    return o;
+  }
+  static __device__ __forceinline__ cx<F> cmul(cx<F> a, cx<F> b)
+  {
+    cx<F> o;
+    o.r = __fma_rn(a.r, b.r, -__dmul_rn(a.i, b.i));
+    o.i = __fma_rn(a.r, b.i, __dmul_rn(a.i, b.r));
+    return o;
+  }
+  /* demodulated recurrence: aux <- (aux + delta) * cw with cw = conj(tw) */
+  static __device__ __forceinline__ cx<F> slide(cx<F> x, cx<F> cw, F d)
+  {
+    const F t = __dadd_rn(x.r, d);
+    cx<F> o;
+    o.r = __fma_rn(t, cw.r, -__dmul_rn(x.i, cw.i));
+    o.i = __fma_rn(t, cw.i, __dmul_rn(x.i, cw.r));
+    return o;
+  }
+  template <int WINDOW>
+  static __device__ __forceinline__ F fast_tap(F l2, F l1, F c, F r1, F r2, const WindowConst<F>& k)
+  {
+    if (WINDOW == 0) return c;
+    else if (WINDOW == 3) return __fma_rn(-k.k1, __dadd_rn(l1, r1), __fma_rn(c, k.k0, __dadd_rn(l2, r2)));
+    else return __fma_rn(c, k.k0, -__dadd_rn(l1, r1));
+  }
+  template <int WINDOW>
+  static __device__ __forceinline__ cx<F> fast_window(cx<F> l2, cx<F> l1, cx<F> c, cx<F> r1, cx<F> r2, const WindowConst<F>& k)
+  {
+    cx<F> o;
+    o.r = fast_tap<WINDOW>(l2.r, l1.r, c.r, r1.r, r2.r, k);
+    o.i = fast_tap<WINDOW>(l2.i, l1.i, c.i, r1.i, r2.i, k);
+    return o;
+  }
 };
-
-/* window taps on one component, sdft.h:350-402; WINDOW follows enum sdft_window */
-template <typename F> struct WindowConst
-{
-  F w;       // analysis weight 1/(2m)                        sdft.h:422
-  F wq;      // w * 0.25, the Hann factor                     sdft.h:371
-  F c0, c1, c2;   // double path: weight folded into the centre / first / second neighbour coefficients
-};
-
-template <typename F>
-inline WindowConst<F> make_window_const(size_t m, int window)
-{
-  WindowConst<F> k;
-  k.w = (F)(1) / (F)(m * 2);
-  k.wq = k.w * (F)(0.25);
-  switch (window)
-  {
-    case 1: k.c0 = (F)2 * k.wq; k.c1 = k.wq; k.c2 = (F)0; break;
-    case 2: k.c0 = (F)(0.54) * k.w; k.c1 = (F)(0.23) * k.w; k.c2 = (F)0; break;
-    case 3: k.c0 = (F)(0.42) * k.w; k.c1 = (F)(0.25) * k.w; k.c2 = (F)(0.04) * k.w; break;
-    default: k.c0 = k.w; k.c1 = (F)0; k.c2 = (F)0; break;
-  }
-  return k;
-}
-
-/* float: the reference's operation order, un-fused */
-template <int WINDOW>
-__device__ __forceinline__ float window_tap(float l2, float l1, float c, float r1, float r2, const WindowConst<float>& k)
-{
-  typedef Arith<float> A;
-  typedef float F;
-  if (WINDOW == 1)
-  {
-    return A::mul(A::sub(A::add(c, c), A::add(l1, r1)), k.wq);
-  }
-  else if (WINDOW == 2)
-  {
-    return A::mul(A::sub(A::mul(c, (F)(0.54)), A::mul(A::add(l1, r1), (F)(0.23))), k.w);
-  }
-  else if (WINDOW == 3)
-  {
-    const F a = A::mul(c, (F)(0.42));
-    const F b = A::mul(A::add(l1, r1), (F)(0.25));
-    const F d = A::mul(A::add(l2, r2), (F)(0.04));
-    return A::mul(A::add(A::sub(a, b), d), k.w);
-  }
-  else
-  {
-    return A::mul(c, k.w);
-  }
-}
-
-/* double: same taps with the weight folded into the coefficients and FMAs (3 / 3 / 5 FP64 instructions
- * per component instead of 4 / 5 / 8); differs from the reference's order by rounding only (~1e-16) */
-template <int WINDOW>
-__device__ __forceinline__ double window_tap(double l2, double l1, double c, double r1, double r2,
-                                             const WindowConst<double>& k)
-{
-  if (WINDOW == 0)
-  {
-    return __dmul_rn(c, k.c0);
-  }
-  else if (WINDOW == 3)
-  {
-    const double t = __fma_rn(c, k.c0, -__dmul_rn(__dadd_rn(l1, r1), k.c1));
-    return __fma_rn(__dadd_rn(l2, r2), k.c2, t);
-  }
-  else
-  {
-    return __fma_rn(c, k.c0, -__dmul_rn(__dadd_rn(l1, r1), k.c1));
-  }
-}
 
 /* ------------------------------------------------------------------------------------------------
  * chunk schedule: identical on host and device
@@ -194,8 +324,9 @@ struct ChunkSpan
 {
   unsigned long long t0;  // first sample (index inside the call)
   unsigned len;           // samples in the chunk (1..L)
-  unsigned f0_row;        // row of the phase table holding P at the chunk's first cursor
-  bool first;             // chunk 0 of the call: phase comes from the plan's saved phase
+  unsigned cursor0;       // cursor before the chunk's first sample: row cursor0/32 of the phase table
+                          // plus cursor0%32 rotations give its phase (0 rotations except for chunk 0)
+  bool first;             // chunk 0 of the call
   bool wraps;             // last step is the period's last step (cursor 2m-1): phase restarts
 };
 
@@ -239,41 +370,10 @@ __host__ __device__ inline ChunkSpan chunk_span(const Schedule& s, unsigned j)
   ChunkSpan c;
   c.t0 = us - s.cursor;
   c.len = (unsigned)(ue - us);
-  c.f0_row = (r * s.chunk) / kF0Stride;
+  c.cursor0 = (unsigned)(us - base);
   c.first = (j == 0);
   c.wraps = (ue == pe);
   return c;
-}
-
-/* mirror cells: source bin (or -1 = always zero) and whether the copy is conjugated.  Resolved on
- * the host from the assignment order of sdft.h:589-595 (matters only for m < 3). */
-struct MirrorMap
-{
-  int cell[4];
-  int src[4];
-  int conj[4];
-};
-
-template <typename F>
-__device__ __forceinline__ void store_with_mirrors(cx<F>* row, unsigned k, cx<F> v, const MirrorMap& mm)
-{
-  row[k + 2] = v;
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-  {
-    if (mm.src[q] == (int)k)
-    {
-      cx<F> c = v;
-      if (mm.conj[q]) c.i = -c.i;
-      row[mm.cell[q]] = c;
-    }
-    else if (mm.src[q] < 0 && k == 0)
-    {
-      cx<F> z;
-      z.r = (F)0; z.i = (F)0;
-      row[mm.cell[q]] = z;
-    }
-  }
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -302,7 +402,7 @@ template <typename T, typename F>
 __global__ void delta_kernel(const T* __restrict__ samples, size_t sample_stride,
                              const T* __restrict__ hist_old, T* __restrict__ hist_new,
                              F* __restrict__ delta, size_t delta_stride,
-                             unsigned long long n, unsigned period)
+                             unsigned long long n, unsigned period, F scale)
 {
   const unsigned ch = blockIdx.y;
   const T* x = samples + (size_t)ch * sample_stride;
@@ -315,7 +415,7 @@ __global__ void delta_kernel(const T* __restrict__ samples, size_t sample_stride
     const T newest = x[t];
     const T oldest = (t < period) ? ho[t] : x[t - period];
     const T diff = newest - oldest;   // T is float or double: one rounding in TD precision
-    d[t] = (F)diff;
+    d[t] = (F)diff * scale;           // scale is exactly 1 unless the window weight is folded in (fast mode)
   }
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < period; i += stride)
   {
@@ -324,145 +424,58 @@ __global__ void delta_kernel(const T* __restrict__ samples, size_t sample_stride
   }
 }
 
-/* ------------------------------------------------------------------------------------------------
- * K2  chunk totals (scan pass 1): S[ch][j][k+2] = sum_i P[c_j + i][k] * delta[t_j + i]
- *     one thread per bin; the last chunk also leaves the plan's phase for the next call
- * ---------------------------------------------------------------------------------------------- */
-template <typename F> struct ScanArgs
-{
-  Schedule sched;
-  const F* delta;          // (channels, delta_stride)
-  size_t delta_stride;
-  const cx<F>* tw_ext;     // (cells)
-  const cx<F>* f0;         // (rows, cells)
-  const cx<F>* phase_in;   // (channels, cells)  P at the cursor the call starts with
-  cx<F>* phase_out;        // (channels, cells)  P at the cursor the call ends with (other buffer)
-  cx<F>* acc_state;        // (channels, cells)
-  cx<F>* totals;           // (channels, nchunks, cells): totals, then carries in place
-  unsigned m;
-  unsigned cells;          // m + 4
-  MirrorMap mirrors;
-};
-
-constexpr int kTotalsThreads = 128;
-
+/* phase at an arbitrary cursor: table row + (cursor % 32) rotations -- the same values the sequential
+ * recurrence of the reference produces (bit-identical for float) */
 template <typename F>
-__global__ void __launch_bounds__(kTotalsThreads) chunk_totals_kernel(const ScanArgs<F> a)
+__device__ __forceinline__ cx<F> phase_at(const cx<F>* __restrict__ f0, unsigned cells, int e, unsigned cursor, cx<F> w)
 {
-  __shared__ F sdelta[kMaxChunk];
-  const unsigned bin_blocks = (a.m + kTotalsThreads - 1) / kTotalsThreads;
-  const unsigned j = blockIdx.x / bin_blocks;
-  const unsigned bb = blockIdx.x - j * bin_blocks;
-  const unsigned ch = blockIdx.y;
-  const ChunkSpan cs = chunk_span(a.sched, j);
+  cx<F> p = f0[(size_t)(cursor / kF0Stride) * cells + e];
+  const unsigned steps = cursor % kF0Stride;
+  for (unsigned i = 0; i < steps; ++i) p = Arith<F>::rotate(p, w);
+  return p;
+}
 
-  const F* dsrc = a.delta + (size_t)ch * a.delta_stride + cs.t0;
-  for (unsigned i = threadIdx.x; i < cs.len; i += kTotalsThreads) sdelta[i] = dsrc[i];
-  __syncthreads();
-
-  const unsigned k = bb * kTotalsThreads + threadIdx.x;
-  if (k >= a.m) return;
-  const unsigned e = k + 2;
-  const cx<F> w = a.tw_ext[e];
-  cx<F> p = cs.first ? a.phase_in[(size_t)ch * a.cells + e] : a.f0[(size_t)cs.f0_row * a.cells + e];
-  cx<F> acc;
-  acc.r = (F)0; acc.i = (F)0;
-  const unsigned body = cs.len - 1;
-#pragma unroll 4
-  for (unsigned i = 0; i < body; ++i)
-  {
-    acc = Arith<F>::mac(acc, p, sdelta[i]);
-    p = Arith<F>::rotate(p, w);
-  }
-  acc = Arith<F>::mac(acc, p, sdelta[body]);
-  a.totals[((size_t)ch * a.sched.nchunks + j) * a.cells + e] = acc;
-
-  if (j == a.sched.nchunks - 1)
-  {
-    p = cs.wraps ? a.f0[e] : Arith<F>::rotate(p, w);   // row 0 of the table is the restart value
-    store_with_mirrors(a.phase_out + (size_t)ch * a.cells, k, p, a.mirrors);
-  }
+/* introspection (sdft_b200_get_state): the modulation phase of every bin at `cursor` */
+template <typename F>
+__global__ void phase_at_kernel(const cx<F>* __restrict__ tw_ext, const cx<F>* __restrict__ f0, cx<F>* __restrict__ out,
+                                unsigned cells, unsigned cursor)
+{
+  const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= cells) return;
+  out[e] = phase_at<F>(f0, cells, (int)e, cursor, tw_ext[e]);
 }
 
 /* ------------------------------------------------------------------------------------------------
- * K2b  exclusive scan of the chunk totals over time, seeded with the plan's accumulators
- *      (the running accoutput of sdft.h:157); totals[] becomes the carry entering each chunk
- * ---------------------------------------------------------------------------------------------- */
-template <typename F>
-__global__ void carry_scan_kernel(const ScanArgs<F> a)
-{
-  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned ch = blockIdx.y;
-  if (k >= a.m) return;
-  cx<F>* acc_row = a.acc_state + (size_t)ch * a.cells;
-  cx<F> run = acc_row[k + 2];
-  cx<F>* base = a.totals + (size_t)ch * a.sched.nchunks * a.cells;
-  const unsigned n = a.sched.nchunks;
-  constexpr int U = 8;
-  unsigned j = 0;
-  for (; j + U <= n; j += U)
-  {
-    cx<F> v[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) v[u] = base[(size_t)(j + u) * a.cells + k + 2];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-    {
-      store_with_mirrors(base + (size_t)(j + u) * a.cells, k, run, a.mirrors);
-      run.r = Arith<F>::add(run.r, v[u].r);
-      run.i = Arith<F>::add(run.i, v[u].i);
-    }
-  }
-  for (; j < n; ++j)
-  {
-    const cx<F> v = base[(size_t)j * a.cells + k + 2];
-    store_with_mirrors(base + (size_t)j * a.cells, k, run, a.mirrors);
-    run.r = Arith<F>::add(run.r, v.r);
-    run.i = Arith<F>::add(run.i, v.i);
-  }
-  store_with_mirrors(acc_row, k, run, a.mirrors);
-}
-
-/* ------------------------------------------------------------------------------------------------
- * K3  emit (scan pass 2, the dominant kernel): replay each chunk from its carry, demodulate, apply
- *     the window across neighbouring cells and stream the (n, m) rows out.
+ * Lane engine of the emit phase: replay a chunk from its carry, demodulate, apply the window across
+ *     neighbouring cells and stream the (n, m) rows out.
  *
- *     One warp owns kWarpCells = 128 consecutive cells (4 per lane) of one chunk and is independent
- *     of every other warp: the 2 outermost cells on either side are halo (recomputed by the
- *     neighbouring warp), so 124 bins per warp are stored (128 for the boxcar window).  Neighbour
- *     cells inside the warp come from registers or one shuffle.  Rows are written with consecutive
- *     lanes on consecutive bins; when m is even each lane stores aligned pairs of bins
- *     (32 B for double, 16 B for float) with an evict-first policy.
+ *     One warp owns Geo<F>::WC consecutive cells (CPL per lane: 128 cells for double, 256 for float) of
+ *     one chunk and is independent of every other warp: the outermost GROUP cells on either side are
+ *     halo (recomputed by the neighbouring warp), so 124 (double) / 248 (float) bins per warp are
+ *     stored; the boxcar window needs no halo.  Neighbour cells inside the warp come from registers
+ *     or one shuffle.  Rows are written with consecutive lanes on consecutive bins, each lane storing
+ *     32-byte groups (2 double or 4 float bins) with an evict-first policy when the row pitch allows
+ *     it, else bin by bin.
  * ---------------------------------------------------------------------------------------------- */
-template <typename F> struct EmitArgs
-{
-  ScanArgs<F> scan;
-  cx<F>* out;              // (channels, n, m)
-  size_t out_channel_stride;   // in complex elements
-  unsigned groups;         // warps needed to cover one row
-  unsigned group_blocks;   // CTAs per chunk
-  WindowConst<F> win;
-};
-
-__device__ __forceinline__ void store_pair(cx<double>* dst, cx<double> a, cx<double> b)
+/* one 32-byte group: 2 double bins or 4 float bins */
+__device__ __forceinline__ void store_group(cx<double>* dst, const cx<double>* y)
 {
   asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.f64 [%0], {%1, %2, %3, %4};"
-               :: "l"(dst), "d"(a.r), "d"(a.i), "d"(b.r), "d"(b.i));
+               :: "l"(dst), "d"(y[0].r), "d"(y[0].i), "d"(y[1].r), "d"(y[1].i));
 }
-__device__ __forceinline__ void store_pair(cx<float>* dst, cx<float> a, cx<float> b)
+__device__ __forceinline__ void store_group(cx<float>* dst, const cx<float>* y)
 {
-  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};"
-               :: "l"(dst), "f"(a.r), "f"(a.i), "f"(b.r), "f"(b.i));
+  asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :: "l"(dst), "f"(y[0].r), "f"(y[0].i), "f"(y[1].r), "f"(y[1].i),
+                  "f"(y[2].r), "f"(y[2].i), "f"(y[3].r), "f"(y[3].i));
 }
 __device__ __forceinline__ void store_one(cx<double>* dst, cx<double> a)
 {
-  asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};"
-               :: "l"(dst), "d"(a.r), "d"(a.i));
+  asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" :: "l"(dst), "d"(a.r), "d"(a.i));
 }
 __device__ __forceinline__ void store_one(cx<float>* dst, cx<float> a)
 {
-  asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};"
-               :: "l"(dst), "f"(a.r), "f"(a.i));
+  asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" :: "l"(dst), "f"(a.r), "f"(a.i));
 }
 
 template <typename F>
@@ -482,138 +495,147 @@ __device__ __forceinline__ cx<F> shfl_down1(cx<F> v)
   return o;
 }
 
+template <typename F, int WINDOW> struct EmitGeo
+{
+  enum
+  {
+    CPL = Geo<F>::CPL,
+    GROUP = Geo<F>::GROUP,
+    NGROUP = CPL / GROUP,
+    WC = Geo<F>::WC,
+    HALO = (WINDOW == 0) ? 0 : (int)GROUP,
+    SPAN = WC - 2 * HALO        // bins stored per warp
+  };
+};
+
 template <typename F, int WINDOW, bool VEC>
 struct EmitLane
 {
-  cx<F> acc[kCellsPerLane];
-  cx<F> ph[kCellsPerLane];
-  cx<F> tw[kCellsPerLane];
+  typedef EmitGeo<F, WINDOW> G;
+  cx<F> acc[G::CPL];
+  cx<F> ph[G::CPL];
+  cx<F> tw[G::CPL];
   cx<F>* dst;            // address of this lane's cell 0 in the current row (may be out of range)
-  bool ok[kCellsPerLane];
+  bool ok[G::CPL];
+
+  /* geometry of lane `lane` of warp-group `group`: first cell index (signed: the float halo reaches
+   * below cell 0) and which of its cells are stored */
+  __device__ __forceinline__ int setup(unsigned group, unsigned lane, unsigned m)
+  {
+    const int e0 = (int)(group * G::SPAN) + 2 - G::HALO + (int)(lane * G::CPL);
+#pragma unroll
+    for (int b = 0; b < G::CPL; ++b)
+    {
+      const int slot = (int)lane * G::CPL + b;
+      const int e = e0 + b;
+      ok[b] = (slot >= G::HALO) && (slot < G::WC - G::HALO) && (e >= 2) && (e < (int)m + 2);
+    }
+    return e0;
+  }
 
   /* one time step; RESTART = the period's last step, after which the phase restarts (sdft.h:566-576) */
   template <bool RESTART>
   __device__ __forceinline__ void step(F d, const cx<F>* restart, const WindowConst<F>& win, size_t row_stride)
   {
     typedef Arith<F> A;
-    cx<F> x[kCellsPerLane];
+    cx<F> x[G::CPL];
 #pragma unroll
-    for (int b = 0; b < kCellsPerLane; ++b)
+    for (int b = 0; b < G::CPL; ++b)
     {
       acc[b] = A::mac(acc[b], ph[b], d);
       ph[b] = RESTART ? restart[b] : A::rotate(ph[b], tw[b]);
       x[b] = A::demod(acc[b], ph[b]);
     }
-    cx<F> y[kCellsPerLane];
+    cx<F> y[G::CPL];
     if (WINDOW == 0)
     {
 #pragma unroll
-      for (int b = 0; b < kCellsPerLane; ++b)
-      {
-        y[b].r = window_tap<0>(x[b].r, x[b].r, x[b].r, x[b].r, x[b].r, win);
-        y[b].i = window_tap<0>(x[b].i, x[b].i, x[b].i, x[b].i, x[b].i, win);
-      }
+      for (int b = 0; b < G::CPL; ++b) y[b] = A::template window<0>(x[b], x[b], x[b], x[b], x[b], win);
     }
     else
     {
-      /* neighbours: [l2 l1 | x0 x1 x2 x3 | r1 r2] */
-      cx<F> l1 = shfl_up1(x[3]);
-      cx<F> r1 = shfl_down1(x[0]);
-      cx<F> l2, r2;
+      /* neighbours: [l2 l1 | x0 .. x(CPL-1) | r1 r2] */
+      const cx<F> l1 = shfl_up1(x[G::CPL - 1]);
+      const cx<F> r1 = shfl_down1(x[0]);
+      cx<F> l2 = l1, r2 = r1;   // only read by the 5-tap window
       if (WINDOW == 3)
       {
-        l2 = shfl_up1(x[2]);
+        l2 = shfl_up1(x[G::CPL - 2]);
         r2 = shfl_down1(x[1]);
       }
-      else
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b)
       {
-        l2 = l1; r2 = r1;   // unused
+        const cx<F> m2 = (b >= 2) ? x[b >= 2 ? b - 2 : 0] : ((b == 1) ? l1 : l2);
+        const cx<F> m1 = (b >= 1) ? x[b >= 1 ? b - 1 : 0] : l1;
+        const cx<F> p1 = (b + 1 < G::CPL) ? x[b + 1 < G::CPL ? b + 1 : 0] : r1;
+        const cx<F> p2 = (b + 2 < G::CPL) ? x[b + 2 < G::CPL ? b + 2 : 0] : ((b + 1 < G::CPL) ? r1 : r2);
+        y[b] = A::template window<WINDOW>(m2, m1, x[b], p1, p2, win);
       }
-      y[0].r = window_tap<WINDOW>(l2.r, l1.r, x[0].r, x[1].r, x[2].r, win);
-      y[0].i = window_tap<WINDOW>(l2.i, l1.i, x[0].i, x[1].i, x[2].i, win);
-      y[1].r = window_tap<WINDOW>(l1.r, x[0].r, x[1].r, x[2].r, x[3].r, win);
-      y[1].i = window_tap<WINDOW>(l1.i, x[0].i, x[1].i, x[2].i, x[3].i, win);
-      y[2].r = window_tap<WINDOW>(x[0].r, x[1].r, x[2].r, x[3].r, r1.r, win);
-      y[2].i = window_tap<WINDOW>(x[0].i, x[1].i, x[2].i, x[3].i, r1.i, win);
-      y[3].r = window_tap<WINDOW>(x[1].r, x[2].r, x[3].r, r1.r, r2.r, win);
-      y[3].i = window_tap<WINDOW>(x[1].i, x[2].i, x[3].i, r1.i, r2.i, win);
     }
     if (VEC)
     {
-      if (ok[0]) store_pair(dst, y[0], y[1]);
-      if (ok[2]) store_pair(dst + 2, y[2], y[3]);
+#pragma unroll
+      for (int g = 0; g < G::NGROUP; ++g)
+        if (ok[g * G::GROUP]) store_group(dst + g * G::GROUP, y + g * G::GROUP);
     }
     else
     {
 #pragma unroll
-      for (int b = 0; b < kCellsPerLane; ++b)
+      for (int b = 0; b < G::CPL; ++b)
+        if (ok[b]) store_one(dst + b, y[b]);
+    }
+    dst += row_stride;
+  }
+
+  /* fast mode (double): acc[] holds the DEMODULATED spectrum, tw[] holds conj(tw); ph[] is unused */
+  __device__ __forceinline__ void fast_step(F d, const WindowConst<F>& win, size_t row_stride)
+  {
+    typedef Arith<F> A;
+#pragma unroll
+    for (int b = 0; b < G::CPL; ++b) acc[b] = A::slide(acc[b], tw[b], d);
+    cx<F> y[G::CPL];
+    if (WINDOW == 0)
+    {
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b) y[b] = acc[b];
+    }
+    else
+    {
+      const cx<F> l1 = shfl_up1(acc[G::CPL - 1]);
+      const cx<F> r1 = shfl_down1(acc[0]);
+      cx<F> l2 = l1, r2 = r1;
+      if (WINDOW == 3)
+      {
+        l2 = shfl_up1(acc[G::CPL - 2]);
+        r2 = shfl_down1(acc[1]);
+      }
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b)
+      {
+        const cx<F> m2 = (b >= 2) ? acc[b >= 2 ? b - 2 : 0] : ((b == 1) ? l1 : l2);
+        const cx<F> m1 = (b >= 1) ? acc[b >= 1 ? b - 1 : 0] : l1;
+        const cx<F> p1 = (b + 1 < G::CPL) ? acc[b + 1 < G::CPL ? b + 1 : 0] : r1;
+        const cx<F> p2 = (b + 2 < G::CPL) ? acc[b + 2 < G::CPL ? b + 2 : 0] : ((b + 1 < G::CPL) ? r1 : r2);
+        y[b] = A::template fast_window<WINDOW>(m2, m1, acc[b], p1, p2, win);
+      }
+    }
+    if (VEC)
+    {
+#pragma unroll
+      for (int g = 0; g < G::NGROUP; ++g)
+        if (ok[g * G::GROUP]) store_group(dst + g * G::GROUP, y + g * G::GROUP);
+    }
+    else
+    {
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b)
         if (ok[b]) store_one(dst + b, y[b]);
     }
     dst += row_stride;
   }
 };
 
-template <typename F, int WINDOW, bool VEC>
-__global__ void __launch_bounds__(kEmitWarps * 32) emit_kernel(const EmitArgs<F> a)
-{
-  constexpr int HALO = (WINDOW == 0) ? 0 : 2;
-  constexpr int SPAN = kWarpCells - 2 * HALO;   // bins stored per warp
-  __shared__ F sdelta[kMaxChunk];
-
-  const ScanArgs<F>& s = a.scan;
-  const unsigned j = blockIdx.x / a.group_blocks;
-  const unsigned gblk = blockIdx.x - j * a.group_blocks;
-  const unsigned ch = blockIdx.y;
-  const ChunkSpan cs = chunk_span(s.sched, j);
-
-  const F* dsrc = s.delta + (size_t)ch * s.delta_stride + cs.t0;
-  for (unsigned i = threadIdx.x; i < cs.len; i += kEmitWarps * 32) sdelta[i] = dsrc[i];
-  __syncthreads();
-
-  const unsigned warp = threadIdx.x >> 5;
-  const unsigned lane = threadIdx.x & 31;
-  const unsigned group = gblk * kEmitWarps + warp;
-  if (group >= a.groups) return;
-
-  /* cell index of this lane's slot 0: the warp's 128 cells start HALO cells below its first bin */
-  const unsigned first_bin = group * SPAN;
-  const unsigned e0 = first_bin + 2 - HALO + lane * kCellsPerLane;
-
-  EmitLane<F, WINDOW, VEC> L;
-  cx<F> restart[kCellsPerLane];
-  const cx<F>* phase_src = cs.first ? s.phase_in + (size_t)ch * s.cells
-                                    : s.f0 + (size_t)cs.f0_row * s.cells;
-  const cx<F>* carry_src = s.totals + ((size_t)ch * s.sched.nchunks + j) * s.cells;
-#pragma unroll
-  for (int b = 0; b < kCellsPerLane; ++b)
-  {
-    const unsigned e = e0 + b;
-    const bool live = e < s.cells;
-    cx<F> z;
-    z.r = (F)0; z.i = (F)0;
-    L.tw[b] = live ? s.tw_ext[e] : z;
-    L.ph[b] = live ? phase_src[e] : z;
-    L.acc[b] = live ? carry_src[e] : z;
-    restart[b] = live ? s.f0[e] : z;
-    /* stored iff the cell is one of the warp's SPAN inner cells and a real bin below m */
-    const unsigned slot = lane * kCellsPerLane + b;
-    const long long k = (long long)e - 2;
-    L.ok[b] = ((int)slot >= HALO) && (slot < (unsigned)(kWarpCells - HALO)) && (e >= 2u) && (k < (long long)s.m);
-  }
-  const size_t row_stride = s.m;
-  L.dst = a.out + (size_t)ch * a.out_channel_stride + (size_t)cs.t0 * row_stride + ((long long)e0 - 2);
-
-  const unsigned body = cs.wraps ? cs.len - 1 : cs.len;
-#pragma unroll 2
-  for (unsigned i = 0; i < body; ++i)
-  {
-    L.template step<false>(sdelta[i], restart, a.win, row_stride);
-  }
-  if (cs.wraps)
-  {
-    L.template step<true>(sdelta[body], restart, a.win, row_stride);
-  }
-}
 
 /* ------------------------------------------------------------------------------------------------
  * K23  single-pass chained scan + emit (the production analysis kernel)
@@ -642,12 +664,10 @@ template <typename F> struct ChainArgs
   size_t delta_stride;
   const cx<F>* tw_ext;     // (cells)
   const cx<F>* f0;         // (rows, cells)
-  const cx<F>* phase_in;   // (channels, cells)
-  cx<F>* phase_out;
   const cx<F>* acc_in;     // (channels, cells)
   cx<F>* acc_out;
-  cx<F>* totals;           // (channels, nchunks, groups, kWarpCells) each chunk's own total
-  cx<F>* prefix;           // (channels, nchunks, groups, kWarpCells) inclusive prefix after each chunk
+  cx<F>* totals;           // (channels, nchunks, groups, Geo<F>::WC) each chunk's own total
+  cx<F>* prefix;           // (channels, nchunks, groups, Geo<F>::WC) inclusive prefix after each chunk
   unsigned* flags;         // (channels, nchunks, groups): 2*epoch = total published, 2*epoch+1 = prefix published
   unsigned* control;       // [0] ticket counter, [1] error flag
   unsigned epoch;
@@ -700,11 +720,28 @@ template <> __device__ __forceinline__ void store_l2<float>(cx<float>* p, cx<flo
   __stcg(reinterpret_cast<float2*>(p), make_float2(v.r, v.i));
 }
 
-template <typename F, int WINDOW, bool VEC, bool EMIT>
+enum { MODE_MODULATED = 0, MODE_FAST = 1 };
+
+/* float never runs the fast mode; these keep the shared kernel body compilable */
+template <typename F, int MODE> struct FastOps
+{
+  static __device__ __forceinline__ cx<F> horner(cx<F> h, cx<F>, F) { return h; }
+  static __device__ __forceinline__ cx<F> cmul(cx<F> a, cx<F>) { return a; }
+  static __device__ __forceinline__ cx<F> demod(cx<F> a, cx<F>) { return a; }
+};
+template <> struct FastOps<double, MODE_FAST>
+{
+  typedef double F;
+  static __device__ __forceinline__ cx<F> horner(cx<F> h, cx<F> w, F d) { return Arith<F>::horner(h, w, d); }
+  static __device__ __forceinline__ cx<F> cmul(cx<F> a, cx<F> b) { return Arith<F>::cmul(a, b); }
+  static __device__ __forceinline__ cx<F> demod(cx<F> a, cx<F> p) { return Arith<F>::demod(a, p); }
+};
+
+template <typename F, int WINDOW, bool VEC, bool EMIT, int MODE>
 __global__ void __launch_bounds__(kEmitWarps * 32, 4) scan_emit_kernel(const ChainArgs<F> a)
 {
-  constexpr int HALO = (WINDOW == 0) ? 0 : 2;
-  constexpr int SPAN = kWarpCells - 2 * HALO;
+  typedef EmitGeo<F, WINDOW> G;
+  typedef Arith<F> A;
   __shared__ F sdelta[kMaxChunk];
   __shared__ unsigned s_ticket;
 
@@ -732,61 +769,66 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) scan_emit_kernel(const Cha
   const unsigned group = gblk * kEmitWarps + warp;
   if (group >= a.groups) return;
 
-  const unsigned first_bin = group * SPAN;
-  const unsigned e0 = first_bin + 2 - HALO + lane * kCellsPerLane;
   const bool last_chunk = (j == a.sched.nchunks - 1);
 
   EmitLane<F, WINDOW, VEC> L;
-  cx<F> restart[kCellsPerLane];
-  cx<F> start[kCellsPerLane];
-  bool live[kCellsPerLane];
-  const cx<F>* phase_src = cs.first ? a.phase_in + (size_t)ch * a.cells : a.f0 + (size_t)cs.f0_row * a.cells;
+  const int e0 = L.setup(group, lane, a.m);
+  bool live[G::CPL];
   cx<F> zero;
   zero.r = (F)0; zero.i = (F)0;
 #pragma unroll
-  for (int b = 0; b < kCellsPerLane; ++b)
+  for (int b = 0; b < G::CPL; ++b)
   {
-    const unsigned e = e0 + b;
-    live[b] = e < a.cells;
+    const int e = e0 + b;
+    live[b] = (e >= 0) && (e < (int)a.cells);
     L.tw[b] = live[b] ? a.tw_ext[e] : zero;
-    start[b] = live[b] ? phase_src[e] : zero;
-    restart[b] = live[b] ? a.f0[e] : zero;
-    const unsigned slot = lane * kCellsPerLane + b;
-    L.ok[b] = ((int)slot >= HALO) && (slot < (unsigned)(kWarpCells - HALO)) && (e >= 2u) && (e < a.m + 2u);
   }
 
   /* ---- phase A: this chunk's total ---- */
-  cx<F> tot[kCellsPerLane];
+  cx<F> tot[G::CPL];
+  if constexpr (MODE == MODE_FAST)
+  {
+    /* total = P_start * sum_i tw^i delta_i, the inner sum by Horner from the chunk's last sample */
+    typedef FastOps<F, MODE> X;
 #pragma unroll
-  for (int b = 0; b < kCellsPerLane; ++b)
-  {
-    tot[b] = zero;
-    L.ph[b] = start[b];
+    for (int b = 0; b < G::CPL; ++b) tot[b] = zero;
+#pragma unroll 2
+    for (int i = (int)cs.len - 1; i >= 0; --i)
+    {
+      const F d = sdelta[i];
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b) tot[b] = X::horner(tot[b], L.tw[b], d);
+    }
+#pragma unroll
+    for (int b = 0; b < G::CPL; ++b)
+    {
+      L.ph[b] = live[b] ? phase_at<F>(a.f0, a.cells, e0 + b, cs.cursor0, L.tw[b]) : zero;
+      tot[b] = X::cmul(L.ph[b], tot[b]);
+    }
   }
+  else
   {
+#pragma unroll
+    for (int b = 0; b < G::CPL; ++b)
+    {
+      tot[b] = zero;
+      L.ph[b] = live[b] ? phase_at<F>(a.f0, a.cells, e0 + b, cs.cursor0, L.tw[b]) : zero;
+    }
     const unsigned body = cs.len - 1;
 #pragma unroll 2
     for (unsigned i = 0; i < body; ++i)
     {
       const F d = sdelta[i];
 #pragma unroll
-      for (int b = 0; b < kCellsPerLane; ++b)
+      for (int b = 0; b < G::CPL; ++b)
       {
-        tot[b] = Arith<F>::mac(tot[b], L.ph[b], d);
-        L.ph[b] = Arith<F>::rotate(L.ph[b], L.tw[b]);
+        tot[b] = A::mac(tot[b], L.ph[b], d);
+        L.ph[b] = A::rotate(L.ph[b], L.tw[b]);
       }
     }
     const F d = sdelta[body];
 #pragma unroll
-    for (int b = 0; b < kCellsPerLane; ++b) tot[b] = Arith<F>::mac(tot[b], L.ph[b], d);
-  }
-  if (last_chunk)
-  {
-    /* phase the next call starts with (sdft.h:573 / :584) */
-    cx<F>* po = a.phase_out + (size_t)ch * a.cells;
-#pragma unroll
-    for (int b = 0; b < kCellsPerLane; ++b)
-      if (live[b]) po[e0 + b] = cs.wraps ? restart[b] : Arith<F>::rotate(L.ph[b], L.tw[b]);
+    for (int b = 0; b < G::CPL; ++b) tot[b] = A::mac(tot[b], L.ph[b], d);
   }
 
   /* ---- carry: decoupled look-back with a deterministic, left-to-right summation ----
@@ -802,15 +844,15 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) scan_emit_kernel(const Cha
   {
     const cx<F>* ai = a.acc_in + (size_t)ch * a.cells;
 #pragma unroll
-    for (int b = 0; b < kCellsPerLane; ++b) L.acc[b] = live[b] ? ai[e0 + b] : zero;
+    for (int b = 0; b < G::CPL; ++b) L.acc[b] = live[b] ? ai[e0 + b] : zero;
   }
   else
   {
     if (!last_chunk)
     {
-      cx<F>* tp = a.totals + item * kWarpCells + lane * kCellsPerLane;
+      cx<F>* tp = a.totals + item * G::WC + lane * G::CPL;
 #pragma unroll
-      for (int b = 0; b < kCellsPerLane; ++b) store_l2<F>(tp + b, tot[b]);
+      for (int b = 0; b < G::CPL; ++b) store_l2<F>(tp + b, tot[b]);
       __threadfence();
       __syncwarp();
       if (lane == 0) st_release_u32(a.flags + item, code_total);
@@ -855,36 +897,42 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) scan_emit_kernel(const Cha
     __threadfence();
     {
       const size_t qi = item - (size_t)(j - q) * item_stride;
-      const cx<F>* pp = a.prefix + qi * kWarpCells + lane * kCellsPerLane;
+      const cx<F>* pp = a.prefix + qi * G::WC + lane * G::CPL;
 #pragma unroll
-      for (int b = 0; b < kCellsPerLane; ++b) L.acc[b] = load_l2<F>(pp + b);
-      for (long long r = q + 1; r < (long long)j; ++r)
+      for (int b = 0; b < G::CPL; ++b) L.acc[b] = load_l2<F>(pp + b);
+      /* rows are fetched four at a time (independent loads in flight), then added in order */
+      const cx<F>* tbase = a.totals + (item - (size_t)j * item_stride) * G::WC + lane * G::CPL;
+      const size_t tstride = item_stride * G::WC;
+      long long r = q + 1;
+      for (; r + 4 <= (long long)j; r += 4)
       {
-        const size_t ri = item - (size_t)(j - r) * item_stride;
-        const cx<F>* tp = a.totals + ri * kWarpCells + lane * kCellsPerLane;
-        cx<F> v[kCellsPerLane];
+        cx<F> v[4][G::CPL];
 #pragma unroll
-        for (int b = 0; b < kCellsPerLane; ++b) v[b] = load_l2<F>(tp + b);
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int b = 0; b < kCellsPerLane; ++b)
-        {
-          L.acc[b].r = Arith<F>::add(L.acc[b].r, v[b].r);
-          L.acc[b].i = Arith<F>::add(L.acc[b].i, v[b].i);
-        }
+          for (int b = 0; b < G::CPL; ++b) v[u][b] = load_l2<F>(tbase + (size_t)(r + u) * tstride + b);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int b = 0; b < G::CPL; ++b) L.acc[b] = A::cadd(L.acc[b], v[u][b]);
+      }
+      for (; r < (long long)j; ++r)
+      {
+        cx<F> v[G::CPL];
+#pragma unroll
+        for (int b = 0; b < G::CPL; ++b) v[b] = load_l2<F>(tbase + (size_t)r * tstride + b);
+#pragma unroll
+        for (int b = 0; b < G::CPL; ++b) L.acc[b] = A::cadd(L.acc[b], v[b]);
       }
     }
   }
 #pragma unroll
-  for (int b = 0; b < kCellsPerLane; ++b)
-  {
-    tot[b].r = Arith<F>::add(L.acc[b].r, tot[b].r);
-    tot[b].i = Arith<F>::add(L.acc[b].i, tot[b].i);
-  }
+  for (int b = 0; b < G::CPL; ++b) tot[b] = A::cadd(L.acc[b], tot[b]);
   if (!last_chunk)
   {
-    cx<F>* pp = a.prefix + item * kWarpCells + lane * kCellsPerLane;
+    cx<F>* pp = a.prefix + item * G::WC + lane * G::CPL;
 #pragma unroll
-    for (int b = 0; b < kCellsPerLane; ++b) store_l2<F>(pp + b, tot[b]);
+    for (int b = 0; b < G::CPL; ++b) store_l2<F>(pp + b, tot[b]);
     __threadfence();
     __syncwarp();
     if (lane == 0) st_release_u32(a.flags + item, code_prefix);
@@ -894,26 +942,48 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) scan_emit_kernel(const Cha
     /* accumulators the next call starts with (sdft.h:157) */
     cx<F>* ao = a.acc_out + (size_t)ch * a.cells;
 #pragma unroll
-    for (int b = 0; b < kCellsPerLane; ++b)
+    for (int b = 0; b < G::CPL; ++b)
       if (live[b]) ao[e0 + b] = tot[b];
   }
 
   /* ---- phase B: replay from the carry and stream the rows out ---- */
   if (EMIT)
   {
-#pragma unroll
-    for (int b = 0; b < kCellsPerLane; ++b) L.ph[b] = start[b];
     const size_t row_stride = a.m;
     L.dst = a.out + (size_t)ch * a.out_channel_stride + (size_t)cs.t0 * row_stride + ((long long)e0 - 2);
-    const unsigned body = cs.wraps ? cs.len - 1 : cs.len;
+    if constexpr (MODE == MODE_FAST)
+    {
+      /* anchor the demodulated spectrum at the carry (L.ph still holds the chunk's starting phase),
+       * then slide; the period's last step needs no special case: conj(tw)^(2m) = 1 */
+      typedef FastOps<F, MODE> X;
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b)
+      {
+        L.acc[b] = X::demod(L.acc[b], L.ph[b]);
+        L.tw[b].i = -L.tw[b].i;
+      }
 #pragma unroll 2
-    for (unsigned i = 0; i < body; ++i)
-    {
-      L.template step<false>(sdelta[i], restart, a.win, row_stride);
+      for (unsigned i = 0; i < cs.len; ++i) L.fast_step(sdelta[i], a.win, row_stride);
     }
-    if (cs.wraps)
+    else
     {
-      L.template step<true>(sdelta[body], restart, a.win, row_stride);
+      /* the starting phase is generated again rather than kept in registers across phase A */
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b)
+        L.ph[b] = live[b] ? phase_at<F>(a.f0, a.cells, e0 + b, cs.cursor0, L.tw[b]) : zero;
+      const unsigned body = cs.wraps ? cs.len - 1 : cs.len;
+#pragma unroll 2
+      for (unsigned i = 0; i < body; ++i)
+      {
+        L.template step<false>(sdelta[i], (const cx<F>*)nullptr, a.win, row_stride);
+      }
+      if (cs.wraps)
+      {
+        cx<F> restart[G::CPL];
+#pragma unroll
+        for (int b = 0; b < G::CPL; ++b) restart[b] = live[b] ? a.f0[e0 + b] : zero;
+        L.template step<true>(sdelta[body], restart, a.win, row_stride);
+      }
     }
   }
 }

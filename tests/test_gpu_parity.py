@@ -90,6 +90,28 @@ def test_chunk_lengths(SDFT, fd, chunk):
             assert rel_err(got, want) <= TOL[fd], (m, n, rel_err(got, want))
 
 
+@pytest.mark.parametrize("window", ["boxcar", "hann", "hamming", "blackman"])
+def test_double_modulated_mode(SDFT, window, monkeypatch):
+    """SDFT_B200_F64=modulated runs the reference's modulated scheme in double as well (the default for
+    double is the demodulated fast replay); both must sit inside the 1e-9 gate, and close to each other."""
+    from oracle import Oracle
+    rng = np.random.default_rng(77)
+    for m in (2, 37, 1000):
+        fast = SDFT(m, window, 0.5, td="f32", fd="f64")
+        monkeypatch.setenv("SDFT_B200_F64", "modulated")
+        exact = SDFT(m, window, 0.5, td="f32", fd="f64")
+        monkeypatch.delenv("SDFT_B200_F64")
+        o = Oracle("f32", "f64", m, window, 0.5)
+        for n in (7, 2 * m + 13, 3000, 1):
+            x = rng.uniform(-1, 1, n).astype(np.float32)
+            want, a, b = o.sdft(x), fast.sdft(x), exact.sdft(x)
+            assert rel_err(b, want) <= 1e-12, (m, n, rel_err(b, want))
+            assert rel_err(a, want) <= 1e-9, (m, n, rel_err(a, want))
+            assert rel_err(a, b) <= 1e-10
+        assert rel_err(fast.state()[2], o.state()[2]) <= 1e-9
+        assert rel_err(exact.state()[2], o.state()[2]) <= 1e-12
+
+
 def test_float_rows_close_to_bit_exact(SDFT):
     """With one chunk per call the float path follows the reference's summation order exactly."""
     from oracle import Oracle

@@ -10,6 +10,7 @@ import numpy as np
 import torch
 
 from sdft_b200 import SDFT
+from bench import ClockSampler
 
 
 def main():
@@ -31,6 +32,8 @@ def main():
     x = (torch.rand(a.n, device="cuda", dtype=torch.float32 if a.td == "f32" else torch.float64) * 2 - 1)
     out = None
     times = []
+    cs = ClockSampler(0)
+    cs.start()
     for r in range(a.reps + 2):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -39,9 +42,10 @@ def main():
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
     t = float(np.median(times[2:]))
+    clk = cs.stop()
     fdb = 16 if a.fd == "f64" else 8
     res = {"n": a.n, "m": a.m, "window": a.window, "fd": a.fd, "chunk": a.chunk, "ms": t,
-           "bin_updates_per_s": a.n * a.m / (t * 1e-3), "GBps": a.n * a.m * fdb / (t * 1e-3) / 1e9}
+           "bin_updates_per_s": a.n * a.m / (t * 1e-3), "GBps": a.n * a.m * fdb / (t * 1e-3) / 1e9, "clocks": clk}
     if a.synth:
         ts = []
         for r in range(a.reps + 2):
