@@ -70,7 +70,9 @@ def measured_peaks():
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 50 ms in the background; start() early (nvidia-smi needs ~100 ms to come
+    up), mark() the timed region, stop() reports only the samples taken inside the marked region."""
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
     NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
@@ -79,6 +81,8 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.file = None
+        self.t0 = None
+        self.t1 = None
 
     def start(self):
         try:
@@ -88,6 +92,20 @@ class ClockSampler:
                  "-lms", "50"], stdout=self.file, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:
+            return None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "power_w": None, "reasons": [], "samples": 0}
@@ -107,15 +125,18 @@ class ClockSampler:
         sm, mx, pw, reasons = [], [], [], set()
         for r in rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
-                for name, v in zip(self.NAMES, r[3:7]):
+                ts = self._stamp(r[0])
+                if self.t0 is not None and ts is not None and (ts < self.t0 or (self.t1 is not None and ts > self.t1 + 0.05)):
+                    continue
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, v in zip(self.NAMES, r[4:8]):
                     if "Active" in v and "Not" not in v:
                         reasons.add(name)
             except Exception:
                 continue
         if sm:
-            out.update({"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w": float(np.median(pw)), "reasons": sorted(reasons),
-                        "samples": len(sm)})
+            out.update({"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w": float(np.median(pw)),
+                        "reasons": sorted(reasons), "samples": len(sm)})
         return out
 
 
@@ -236,21 +257,23 @@ def run_b200_arm(args, rank, local_rank, world):
         p._f("isdft_n")(p._h, n, op, yp)
 
     # ---- analysis: value + roofline --------------------------------------------------------------
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for _ in range(args.warmup):
         analysis_step()
     for p in plans:
         p._check()
         p._lib.sdft_b200_set_profiling(p._h, 1)
     launches0 = sum(p.launches for p in plans)
-    clocks = ClockSampler(local_rank)
     barrier()
-    clocks.start()
+    clocks.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         analysis_step()
     e1.record()
     torch.cuda.synchronize()
+    clocks.mark_end()
     barrier()
     clk = clocks.stop()
     t_analysis = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
@@ -379,7 +402,7 @@ def run_b200_arm(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=N_SAMPLES, help="samples per window (default 2^20)")

@@ -117,6 +117,30 @@ class Oracle(_Base):
             self.h, d.shape[0], _ptr(d), _ptr(y))
         return y
 
+    def advance(self, x):
+        """State update only (same arithmetic as sdft, no rows): used to walk long signals."""
+        x = self._as_td(x)
+        self._fn("advance_n", None, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p])(self.h, x.size, _ptr(x))
+
+    def clone(self, window=None):
+        """Deep copy of the plan and its state, optionally with another window."""
+        other = Oracle.__new__(Oracle)
+        other.lib = self.lib
+        other._setup(self.td, self.fd, self.m, self.window if window is None else window, self.latency)
+        other.sfx = self.sfx
+        f = self._fn("clone", ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int])
+        other.h = ctypes.c_void_p(f(self.h, other.window))
+        return other
+
+    def roundtrip(self, x):
+        """isdft(sdft(x)) sample by sample without keeping the matrix."""
+        x = self._as_td(x)
+        y = np.empty(x.size, self.td_np)
+        row = np.empty(2 * self.m, self.fd_np)
+        self._fn("roundtrip_n", None, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p])(
+            self.h, x.size, _ptr(x), _ptr(y), _ptr(row))
+        return y
+
     def twiddles(self):
         a = np.empty(self.m, self.fdx_np)
         s = np.empty(self.m, self.fdx_np)

@@ -262,6 +262,76 @@ void OR_FN(isdft_n)(OR_PLAN* p, size_t n, const OR_FD* dfts, OR_TD* samples)
   }
 }
 
+/* ---- helpers for the full-size parity tests (tests/test_gpu_configs.py) ----
+ * The CPU cannot afford to produce every row of a 2^20 x 4096 matrix, so the tests walk the state
+ * through the whole signal and produce rows only at sampled positions.  None of these change the
+ * arithmetic: `advance_n` performs exactly the state updates of one analysis step (sdft.h:564-587)
+ * and skips the demodulation / mirror / window stages, which only feed the output row. */
+void OR_FN(advance_n)(OR_PLAN* p, size_t n, const OR_TD* samples)
+{
+  const size_t m = p->m;
+  const size_t period = 2 * m;
+  for (size_t t = 0; t < n; ++t)
+  {
+    const OR_TD sample = samples[t];
+    const OR_TD oldest = p->history[p->head];
+    p->history[p->head] = sample;
+    p->head = (p->head + 1 == period) ? 0 : p->head + 1;
+    const OR_TD tdelta = sample - oldest;                 /* sdft.h:564 */
+    const OR_FD delta = (OR_FD)tdelta;
+    const int wrap = (p->cursor >= period - 1);
+    p->cursor = wrap ? 0 : p->cursor + 1;
+    for (size_t k = 0; k < m; ++k)
+    {
+      const OR_FD tr = p->ph_re[k] * delta;               /* sdft.h:572 / :583 */
+      const OR_FD ti = p->ph_im[k] * delta;
+      p->acc_re[k] = p->acc_re[k] + tr;
+      p->acc_im[k] = p->acc_im[k] + ti;
+      if (wrap)
+      {
+        p->ph_re[k] = (OR_FD)1;                           /* sdft.h:573 */
+        p->ph_im[k] = (OR_FD)0;
+      }
+      else
+      {
+        const OR_FD pr = p->ph_re[k], pi = p->ph_im[k];   /* sdft.h:584 */
+        const OR_FD wr = p->tw_re[k], wi = p->tw_im[k];
+        p->ph_re[k] = pr * wr - pi * wi;
+        p->ph_im[k] = pr * wi + pi * wr;
+      }
+    }
+  }
+}
+
+/* deep copy of a plan, optionally with another window (the window only enters the output stage,
+ * sdft.h:597, so plans that differ in nothing but the window share their state evolution) */
+OR_PLAN* OR_FN(clone)(const OR_PLAN* src, int window)
+{
+  OR_PLAN* p = OR_FN(alloc)(src->m, window < 0 ? src->window : window, src->latency);
+  const size_t m = src->m;
+  p->cursor = src->cursor;
+  p->head = src->head;
+  memcpy(p->history, src->history, 2 * m * sizeof(OR_TD));
+  memcpy(p->acc_re, src->acc_re, m * sizeof(OR_FD));
+  memcpy(p->acc_im, src->acc_im, m * sizeof(OR_FD));
+  memcpy(p->ph_re, src->ph_re, m * sizeof(OR_FD));
+  memcpy(p->ph_im, src->ph_im, m * sizeof(OR_FD));
+  memcpy(p->ext_re, src->ext_re, (m + 4) * sizeof(OR_FD));
+  memcpy(p->ext_im, src->ext_im, (m + 4) * sizeof(OR_FD));
+  return p;
+}
+
+/* analysis immediately followed by synthesis, sample by sample (the test/test.c:79-80 pattern with a
+ * hop of one): y[t] = isdft(sdft(x[t])).  `row` is caller scratch of 2m OR_FD values. */
+void OR_FN(roundtrip_n)(OR_PLAN* p, size_t n, const OR_TD* samples, OR_TD* out, OR_FD* row)
+{
+  for (size_t t = 0; t < n; ++t)
+  {
+    OR_FN(step)(p, samples[t], row);
+    out[t] = OR_FN(synth)(p, row);
+  }
+}
+
 /* ---- introspection used by the table/state parity tests ---- */
 
 size_t OR_FN(size)(const OR_PLAN* p) { return p ? p->m : 0; }

@@ -40,15 +40,18 @@ def stale():
     return any(os.path.getmtime(d) > t for d in DEPENDS if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, out=None, extra=()):
+    """Builds the library.  `out`/`extra` build an experimental variant (other file name, extra nvcc
+    flags such as -DSDFT_B200_MINBLOCKS=5) that is selected at run time with SDFT_B200_LIB=<path>."""
+    target = out or LIB
+    if out is None and not force and not stale():
         return LIB
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libsdft_b200.so (there is no CPU fallback)")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + SOURCES
     subprocess.run(cmd, check=True)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

@@ -61,6 +61,7 @@ struct sdft_b200_plan
 
   size_t cursor = 0;
   size_t forced_chunk = 0;
+  unsigned forced_warps = 0;     // SDFT_B200_WARPS: warps per scan/emit CTA (0 = choose per plan geometry)
   size_t tile_bytes = 0;
   unsigned long long launches = 0;
 
@@ -78,7 +79,7 @@ struct sdft_b200_plan
   int acc_sel = 0;
   void* phase_scratch = nullptr;   // cells complex values, introspection only
 
-  Buffer samples, deltas, synth_out, tile[2];
+  Buffer samples, synth_out, tile[2];
   Buffer prefix, chain_totals, flags;   // chained scan: inclusive prefixes, chunk totals, epoch-stamped flags
   unsigned* control = nullptr;   // [0] work ticket, [1] spin-wait timeout flag
   unsigned epoch = 0;
@@ -323,7 +324,7 @@ void plan_destroy(Plan* p)
   if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
   void* ptrs[] = { p->tw_ext, p->tws, p->f0, p->history[0], p->history[1], p->acc_state[0], p->acc_state[1], p->phase_scratch,
                    p->prefix.ptr, p->chain_totals.ptr, p->flags.ptr, p->control,
-                   p->samples.ptr, p->deltas.ptr, p->synth_out.ptr, p->tile[0].ptr, p->tile[1].ptr };
+                   p->samples.ptr, p->synth_out.ptr, p->tile[0].ptr, p->tile[1].ptr };
   for (void* q : ptrs)
     if (q) cudaFree(q);
   for (int w = 0; w < 2; ++w)
@@ -368,13 +369,26 @@ Plan* plan_create(size_t m, int window, double latency, size_t channels)
   p->mirrors = make_mirrors(m);
   p->tile_bytes = env_size("SDFT_B200_TILE_MB", 128) << 20;
   p->forced_chunk = env_size("SDFT_B200_CHUNK", 0);
+  p->forced_warps = (unsigned)env_size("SDFT_B200_WARPS", 0);
+  if (p->forced_warps > (unsigned)kEmitWarps) p->forced_warps = kEmitWarps;
   {
-    /* double frequency domain: fast (demodulated replay) unless SDFT_B200_F64=modulated; float always
-     * follows the reference's modulated scheme operation by operation */
-    const char* md = getenv("SDFT_B200_F64");
-    const bool modulated = md && !strcmp(md, "modulated");
-    p->mode = (type_id<F>::value == kF64 && !modulated) ? MODE_FAST : MODE_MODULATED;
-    p->prescale = (p->mode == MODE_FAST) ? (double)make_window_const<double>(m, window).pre : 1.0;
+    /* double frequency domain: fast (demodulated replay) unless SDFT_B200_F64=modulated.
+     * float: the reference's modulated scheme, every rounding kept (rows are bit-exact within a chunk).
+     * SDFT_B200_F32=fused fuses the accumulate / demodulate / window stages (FFMA2, ~5 % faster): the
+     * phase recurrence stays bit-exact, but rows that are pure cancellation noise (the first samples
+     * after a reset under a Blackman window) then carry OTHER noise than the reference's, which the
+     * per-call 1e-4 gate of the parity tests does not accept -- hence opt-in. */
+    if (type_id<F>::value == kF64)
+    {
+      const char* md = getenv("SDFT_B200_F64");
+      p->mode = (md && !strcmp(md, "modulated")) ? MODE_MODULATED : MODE_FAST;
+    }
+    else
+    {
+      const char* md = getenv("SDFT_B200_F32");
+      p->mode = (md && !strcmp(md, "fused")) ? MODE_FAST : MODE_MODULATED;
+    }
+    p->prescale = (p->mode == MODE_FAST && type_id<F>::value == kF64) ? (double)make_window_const<double>(m, window).pre : 1.0;
   }
 
   bool ok = true;
@@ -453,30 +467,25 @@ unsigned choose_chunk(const Plan* p, size_t n)
 }
 
 template <typename F, bool EMIT>
-void launch_chain(Plan* p, const ChainArgs<F>& a, bool vec)
+void launch_chain(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps)
 {
   const dim3 grid(a.total_blocks);
 #define SDFT_CHAIN_CASE(W, MODE)                                                                       \
   case W:                                                                                              \
-    if (vec) scan_emit_kernel<F, W, true, EMIT, MODE><<<grid, kEmitWarps * 32, 0, p->stream>>>(a);     \
-    else scan_emit_kernel<F, W, false, EMIT, MODE><<<grid, kEmitWarps * 32, 0, p->stream>>>(a);        \
+    if (vec) scan_emit_kernel<F, W, true, EMIT, MODE><<<grid, warps * 32, 0, p->stream>>>(a);          \
+    else scan_emit_kernel<F, W, false, EMIT, MODE><<<grid, warps * 32, 0, p->stream>>>(a);             \
     break;
-  bool launched = false;
-  if constexpr (sizeof(F) == sizeof(double))
+  if (p->mode == MODE_FAST)
   {
-    if (p->mode == MODE_FAST)
+    switch (p->window)
     {
-      launched = true;
-      switch (p->window)
-      {
-        SDFT_CHAIN_CASE(0, MODE_FAST)
-        SDFT_CHAIN_CASE(1, MODE_FAST)
-        SDFT_CHAIN_CASE(2, MODE_FAST)
-        SDFT_CHAIN_CASE(3, MODE_FAST)
-      }
+      SDFT_CHAIN_CASE(0, MODE_FAST)
+      SDFT_CHAIN_CASE(1, MODE_FAST)
+      SDFT_CHAIN_CASE(2, MODE_FAST)
+      SDFT_CHAIN_CASE(3, MODE_FAST)
     }
   }
-  if (!launched)
+  else
   {
     switch (p->window)
     {
@@ -490,7 +499,20 @@ void launch_chain(Plan* p, const ChainArgs<F>& a, bool vec)
   p->launches++;
 }
 
-/* production path: K1 + the single-pass chained scan/emit kernel */
+/* warps per scan/emit CTA: the widest CTA (<= kEmitWarps) that leaves the fewest idle warp slots in
+ * the last CTA of a chunk (34 groups -> 2 warps, 17 -> 1, 32 -> 4) */
+unsigned emit_warps_for(unsigned groups)
+{
+  unsigned best = 1, best_waste = 0;
+  for (unsigned w = 2; w <= (unsigned)kEmitWarps; ++w)
+  {
+    const unsigned waste = ((groups + w - 1) / w) * w - groups;
+    if (waste <= best_waste) { best = w; best_waste = waste; }
+  }
+  return best;
+}
+
+/* production path: the single-pass chained scan/emit kernel (deltas and history are its prologue) */
 template <typename T, typename F>
 bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride)
 {
@@ -499,7 +521,8 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   const unsigned chunk = choose_chunk(p, n);
   const Schedule sched = make_schedule(p->cursor, n, m, chunk);
   const unsigned groups = groups_for(p);
-  const unsigned group_blocks = (groups + kEmitWarps - 1) / kEmitWarps;
+  const unsigned warps = p->forced_warps ? p->forced_warps : emit_warps_for(groups);
+  const unsigned group_blocks = (groups + warps - 1) / warps;
   const size_t items = (size_t)ch * sched.nchunks * groups;
   const size_t blocks = (size_t)ch * sched.nchunks * group_blocks;
   if (blocks >= (1ull << 31))
@@ -508,7 +531,6 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
     return false;
   }
 
-  if (!reserve(p, p->deltas, (size_t)ch * n * sizeof(F))) return false;
   if (!reserve(p, p->prefix, items * Geo<F>::WC * sizeof(cx<F>))) return false;
   if (!reserve(p, p->chain_totals, items * Geo<F>::WC * sizeof(cx<F>))) return false;
   const size_t flags_before = p->flags.bytes;
@@ -520,21 +542,14 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   }
   p->epoch++;
 
-  {
-    const size_t work = n > 2 * (size_t)m ? n : 2 * (size_t)m;
-    unsigned kblocks = (unsigned)((work + 255) / 256);
-    if (kblocks > 2048) kblocks = 2048;
-    delta_kernel<T, F><<<dim3(kblocks, ch), 256, 0, p->stream>>>(
-        x, x_stride, (const T*)p->history[p->hist_sel], (T*)p->history[p->hist_sel ^ 1],
-        (F*)p->deltas.ptr, n, n, 2 * m, (F)p->prescale);
-    p->launches++;
-    p->hist_sel ^= 1;
-  }
-
   ChainArgs<F> a;
   a.sched = sched;
-  a.delta = (const F*)p->deltas.ptr;
-  a.delta_stride = n;
+  a.samples = x;
+  a.sample_stride = x_stride;
+  a.hist_old = p->history[p->hist_sel];
+  a.hist_new = p->history[p->hist_sel ^ 1];
+  a.td_double = (type_id<T>::value == kF64) ? 1 : 0;
+  a.scale = (F)p->prescale;
   a.tw_ext = (const cx<F>*)p->tw_ext;
   a.f0 = (const cx<F>*)p->f0;
   a.acc_in = (const cx<F>*)p->acc_state[p->acc_sel];
@@ -556,14 +571,15 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   {
     const bool vec = can_vectorize<F>(m, out, out_stride);
     prof_mark(p, 0);
-    launch_chain<F, true>(p, a, vec);
+    launch_chain<F, true>(p, a, vec, warps);
     prof_mark(p, 0);
   }
   else
   {
-    launch_chain<F, false>(p, a, false);
+    launch_chain<F, false>(p, a, false, warps);
   }
   CU_TRY(p, cudaGetLastError());
+  p->hist_sel ^= 1;
   p->cursor = (size_t)((p->cursor + n) % (2 * (size_t)m));
   p->acc_sel ^= 1;
   return true;

@@ -40,7 +40,10 @@ namespace sdftb200
 constexpr int kF0Stride = 32;     // phase table holds P at every 32nd cursor
 constexpr int kMaxChunk = 1024;   // longest chunk the kernels accept (samples)
 constexpr int kAutoChunk = 512;   // longest chunk the heuristic picks (measured best on B200)
-constexpr int kEmitWarps = 4;     // warps per emit CTA
+constexpr int kEmitWarps = 4;     // most warps per scan/emit CTA (the launch picks 1..4, see emit_warps_for)
+#ifndef SDFT_B200_MINBLOCKS
+#define SDFT_B200_MINBLOCKS 4     // resident 128-thread CTAs per SM the register allocation must allow
+#endif
 
 template <typename F> struct cx { F r, i; };
 
@@ -131,9 +134,49 @@ __device__ __forceinline__ cx<float> pk_sub(cx<float> a, cx<float> b)
   return o;
 }
 
+__device__ __forceinline__ cx<float> pk_fma(cx<float> a, cx<float> b, cx<float> c)   // (a.r*b.r+c.r, a.i*b.i+c.i)
+{
+  cx<float> o;
+  asm("{.reg .b64 x, y, z, w; mov.b64 x, {%2, %3}; mov.b64 y, {%4, %5}; mov.b64 z, {%6, %7}; fma.rn.f32x2 w, x, y, z; mov.b64 {%0, %1}, w;}"
+      : "=f"(o.r), "=f"(o.i) : "f"(a.r), "f"(a.i), "f"(b.r), "f"(b.i), "f"(c.r), "f"(c.i));
+  return o;
+}
+__device__ __forceinline__ cx<float> pk_fma_s(cx<float> a, float k, cx<float> c)           // (a.r*k+c.r, a.i*k+c.i)
+{
+  cx<float> o;
+  asm("{.reg .b64 x, y, z, w; mov.b64 x, {%2, %3}; mov.b64 y, {%4, %4}; mov.b64 z, {%5, %6}; fma.rn.f32x2 w, x, y, z; mov.b64 {%0, %1}, w;}"
+      : "=f"(o.r), "=f"(o.i) : "f"(a.r), "f"(a.i), "f"(k), "f"(c.r), "f"(c.i));
+  return o;
+}
+
 template <> struct Arith<float>
 {
   typedef float F;
+  /* ---- fused variants (MODE_FAST): only used where the result is NOT fed back into the modulation
+   * phase.  The phase recurrence `rotate` stays un-fused in every mode: its rounding compounds over up
+   * to 2m-1 steps and must be the reference's bit for bit; a fused accumulate or a fused
+   * output stage moves a value by <= 1 ulp, the same order as the chunked summation order does. ---- */
+  static __device__ __forceinline__ cx<F> mac_fused(cx<F> acc, cx<F> p, F d) { return pk_fma_s(p, d, acc); }
+  static __device__ __forceinline__ cx<F> demod_fused(cx<F> a, cx<F> p)
+  {
+    /* (ar*pr + ai*pi, ai*pr - ar*pi) */
+    cx<F> sw, np;
+    sw.r = a.i; sw.i = a.r;
+    np.r = p.i; np.i = -p.i;
+    const cx<F> u = pk_mul(sw, np);          // (ai*pi, -ar*pi)
+    cx<F> pr;
+    pr.r = p.r; pr.i = p.r;
+    return pk_fma(a, pr, u);
+  }
+  template <int WINDOW>
+  static __device__ __forceinline__ cx<F> window_fused(cx<F> l2, cx<F> l1, cx<F> c, cx<F> r1, cx<F> r2, const WindowConst<F>& k)
+  {
+    if (WINDOW == 0) return pk_scale(c, k.c0);
+    const cx<F> s1 = pk_scale(pk_add(l1, r1), -k.c1);
+    cx<F> y = pk_fma_s(c, k.c0, s1);
+    if (WINDOW == 3) y = pk_fma_s(pk_add(l2, r2), k.c2, y);
+    return y;
+  }
   static __device__ __forceinline__ cx<F> cadd(cx<F> a, cx<F> b)
   {
     cx<F> o;
@@ -273,6 +316,17 @@ template <> struct Arith<double>
     o.i = __fma_rn(h.r, w.i, __dmul_rn(h.i, w.r));
     return o;
   }
+  /* four Horner steps at once: h <- h * tw^4 + (d0 + d1 tw + d2 tw^2 + d3 tw^3); 10 instead of 16
+   * FP64 instructions */
+  static __device__ __forceinline__ cx<F> horner4(cx<F> h, cx<F> w1, cx<F> w2, cx<F> w3, cx<F> w4, F d0, F d1, F d2, F d3)
+  {
+    const F ir = __fma_rn(d3, w3.r, __fma_rn(d2, w2.r, __fma_rn(d1, w1.r, d0)));
+    const F ii = __fma_rn(d3, w3.i, __fma_rn(d2, w2.i, __dmul_rn(d1, w1.i)));
+    cx<F> o;
+    o.r = __fma_rn(h.r, w4.r, __fma_rn(-h.i, w4.i, ir));
+    o.i = __fma_rn(h.r, w4.i, __fma_rn(h.i, w4.r, ii));
+    return o;
+  }
   static __device__ __forceinline__ cx<F> cmul(cx<F> a, cx<F> b)
   {
     cx<F> o;
@@ -394,36 +448,6 @@ __global__ void phase_table_kernel(const cx<F>* __restrict__ tw_ext, const cx<F>
   }
 }
 
-/* ------------------------------------------------------------------------------------------------
- * K1  deltas in TIME-DOMAIN precision (sdft.h:564) and the new 2m-sample history
- *     ext(t) = history[t] for t < 2m, samples[t - 2m] otherwise; delta[t] = ext(t + 2m) - ext(t)
- * ---------------------------------------------------------------------------------------------- */
-template <typename T, typename F>
-__global__ void delta_kernel(const T* __restrict__ samples, size_t sample_stride,
-                             const T* __restrict__ hist_old, T* __restrict__ hist_new,
-                             F* __restrict__ delta, size_t delta_stride,
-                             unsigned long long n, unsigned period, F scale)
-{
-  const unsigned ch = blockIdx.y;
-  const T* x = samples + (size_t)ch * sample_stride;
-  const T* ho = hist_old + (size_t)ch * period;
-  T* hn = hist_new + (size_t)ch * period;
-  F* d = delta + (size_t)ch * delta_stride;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
-  {
-    const T newest = x[t];
-    const T oldest = (t < period) ? ho[t] : x[t - period];
-    const T diff = newest - oldest;   // T is float or double: one rounding in TD precision
-    d[t] = (F)diff * scale;           // scale is exactly 1 unless the window weight is folded in (fast mode)
-  }
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < period; i += stride)
-  {
-    const unsigned long long pos = n + i;   // position inside history ‖ samples
-    hn[i] = (pos < period) ? ho[pos] : x[pos - period];
-  }
-}
-
 /* phase at an arbitrary cursor: table row + (cursor % 32) rotations -- the same values the sequential
  * recurrence of the reference produces (bit-identical for float) */
 template <typename F>
@@ -495,6 +519,30 @@ __device__ __forceinline__ cx<F> shfl_down1(cx<F> v)
   return o;
 }
 
+/* accumulate / demodulate / window stages of the modulated replay: the reference's own roundings, or
+ * (float MODE_FAST) the fused forms */
+template <typename F, bool FUSED> struct StageOps
+{
+  static __device__ __forceinline__ cx<F> mac(cx<F> acc, cx<F> p, F d) { return Arith<F>::mac(acc, p, d); }
+  static __device__ __forceinline__ cx<F> demod(cx<F> a, cx<F> p) { return Arith<F>::demod(a, p); }
+  template <int WINDOW>
+  static __device__ __forceinline__ cx<F> window(cx<F> l2, cx<F> l1, cx<F> c, cx<F> r1, cx<F> r2, const WindowConst<F>& k)
+  {
+    return Arith<F>::template window<WINDOW>(l2, l1, c, r1, r2, k);
+  }
+};
+template <> struct StageOps<float, true>
+{
+  typedef float F;
+  static __device__ __forceinline__ cx<F> mac(cx<F> acc, cx<F> p, F d) { return Arith<F>::mac_fused(acc, p, d); }
+  static __device__ __forceinline__ cx<F> demod(cx<F> a, cx<F> p) { return Arith<F>::demod_fused(a, p); }
+  template <int WINDOW>
+  static __device__ __forceinline__ cx<F> window(cx<F> l2, cx<F> l1, cx<F> c, cx<F> r1, cx<F> r2, const WindowConst<F>& k)
+  {
+    return Arith<F>::template window_fused<WINDOW>(l2, l1, c, r1, r2, k);
+  }
+};
+
 template <typename F, int WINDOW> struct EmitGeo
 {
   enum
@@ -534,23 +582,24 @@ struct EmitLane
   }
 
   /* one time step; RESTART = the period's last step, after which the phase restarts (sdft.h:566-576) */
-  template <bool RESTART>
+  template <bool RESTART, bool FUSED>
   __device__ __forceinline__ void step(F d, const cx<F>* restart, const WindowConst<F>& win, size_t row_stride)
   {
     typedef Arith<F> A;
+    typedef StageOps<F, FUSED> S;
     cx<F> x[G::CPL];
 #pragma unroll
     for (int b = 0; b < G::CPL; ++b)
     {
-      acc[b] = A::mac(acc[b], ph[b], d);
+      acc[b] = S::mac(acc[b], ph[b], d);
       ph[b] = RESTART ? restart[b] : A::rotate(ph[b], tw[b]);
-      x[b] = A::demod(acc[b], ph[b]);
+      x[b] = S::demod(acc[b], ph[b]);
     }
     cx<F> y[G::CPL];
     if (WINDOW == 0)
     {
 #pragma unroll
-      for (int b = 0; b < G::CPL; ++b) y[b] = A::template window<0>(x[b], x[b], x[b], x[b], x[b], win);
+      for (int b = 0; b < G::CPL; ++b) y[b] = S::template window<0>(x[b], x[b], x[b], x[b], x[b], win);
     }
     else
     {
@@ -570,7 +619,7 @@ struct EmitLane
         const cx<F> m1 = (b >= 1) ? x[b >= 1 ? b - 1 : 0] : l1;
         const cx<F> p1 = (b + 1 < G::CPL) ? x[b + 1 < G::CPL ? b + 1 : 0] : r1;
         const cx<F> p2 = (b + 2 < G::CPL) ? x[b + 2 < G::CPL ? b + 2 : 0] : ((b + 1 < G::CPL) ? r1 : r2);
-        y[b] = A::template window<WINDOW>(m2, m1, x[b], p1, p2, win);
+        y[b] = S::template window<WINDOW>(m2, m1, x[b], p1, p2, win);
       }
     }
     if (VEC)
@@ -660,8 +709,12 @@ struct EmitLane
 template <typename F> struct ChainArgs
 {
   Schedule sched;
-  const F* delta;          // (channels, delta_stride)
-  size_t delta_stride;
+  const void* samples;     // (channels, sample_stride) time-domain samples of this call, float or double
+  size_t sample_stride;
+  const void* hist_old;    // (channels, 2m) the 2m samples before this call, oldest first
+  void* hist_new;          // (channels, 2m) the 2m samples ending with this call's last one
+  int td_double;           // time-domain type of samples/history: 0 float, 1 double
+  F scale;                 // factor folded into the deltas (exactly 1 unless double MODE_FAST folds the window weight)
   const cx<F>* tw_ext;     // (cells)
   const cx<F>* f0;         // (rows, cells)
   const cx<F>* acc_in;     // (channels, cells)
@@ -726,6 +779,7 @@ enum { MODE_MODULATED = 0, MODE_FAST = 1 };
 template <typename F, int MODE> struct FastOps
 {
   static __device__ __forceinline__ cx<F> horner(cx<F> h, cx<F>, F) { return h; }
+  static __device__ __forceinline__ cx<F> horner4(cx<F> h, cx<F>, cx<F>, cx<F>, cx<F>, F, F, F, F) { return h; }
   static __device__ __forceinline__ cx<F> cmul(cx<F> a, cx<F>) { return a; }
   static __device__ __forceinline__ cx<F> demod(cx<F> a, cx<F>) { return a; }
 };
@@ -733,16 +787,60 @@ template <> struct FastOps<double, MODE_FAST>
 {
   typedef double F;
   static __device__ __forceinline__ cx<F> horner(cx<F> h, cx<F> w, F d) { return Arith<F>::horner(h, w, d); }
+  static __device__ __forceinline__ cx<F> horner4(cx<F> h, cx<F> w1, cx<F> w2, cx<F> w3, cx<F> w4, F d0, F d1, F d2, F d3)
+  {
+    return Arith<F>::horner4(h, w1, w2, w3, w4, d0, d1, d2, d3);
+  }
   static __device__ __forceinline__ cx<F> cmul(cx<F> a, cx<F> b) { return Arith<F>::cmul(a, b); }
   static __device__ __forceinline__ cx<F> demod(cx<F> a, cx<F> p) { return Arith<F>::demod(a, p); }
 };
 
+/* K1 (fused prologue)  deltas of one chunk in TIME-DOMAIN precision (sdft.h:564, :186-191):
+ *     ext(t) = history[t] for t < 2m, samples[t - 2m] otherwise; delta[t] = ext(t + 2m) - ext(t),
+ *     one rounding in T, then widened to F. */
+template <typename T, typename F>
+__device__ __forceinline__ void chunk_deltas(const ChainArgs<F>& a, unsigned ch, const ChunkSpan& cs, F* sdelta)
+{
+  const unsigned period = a.sched.period;
+  const T* x = (const T*)a.samples + (size_t)ch * a.sample_stride;
+  const T* ho = (const T*)a.hist_old + (size_t)ch * period;
+  for (unsigned i = threadIdx.x; i < cs.len; i += blockDim.x)
+  {
+    const unsigned long long t = cs.t0 + i;
+    const T newest = x[t];
+    const T oldest = (t < period) ? ho[t] : x[t - period];
+    const T diff = newest - oldest;
+    sdelta[i] = (F)diff * a.scale;
+  }
+}
+/* the history the next call starts from; entries are dealt out over the chunks of the call */
+template <typename T, typename F>
+__device__ __forceinline__ void roll_history(const ChainArgs<F>& a, unsigned ch, unsigned j)
+{
+  const unsigned period = a.sched.period;
+  const T* x = (const T*)a.samples + (size_t)ch * a.sample_stride;
+  const T* ho = (const T*)a.hist_old + (size_t)ch * period;
+  T* hn = (T*)a.hist_new + (size_t)ch * period;
+  for (unsigned i = j * blockDim.x + threadIdx.x; i < period; i += a.sched.nchunks * blockDim.x)
+  {
+    const unsigned long long pos = a.sched.n + i;   // position inside history || samples
+    hn[i] = (pos < period) ? ho[pos] : x[pos - period];
+  }
+}
+
+/* true when the kernel variant <F, MODE> uses the demodulated double replay */
+template <typename F, int MODE> struct IsSlide { enum { value = 0 }; };
+template <> struct IsSlide<double, MODE_FAST> { enum { value = 1 }; };
+
 template <typename F, int WINDOW, bool VEC, bool EMIT, int MODE>
-__global__ void __launch_bounds__(kEmitWarps * 32, 4) scan_emit_kernel(const ChainArgs<F> a)
+__global__ void __launch_bounds__(kEmitWarps * 32, SDFT_B200_MINBLOCKS) scan_emit_kernel(const ChainArgs<F> a)
 {
   typedef EmitGeo<F, WINDOW> G;
   typedef Arith<F> A;
-  __shared__ F sdelta[kMaxChunk];
+  constexpr bool SLIDE = IsSlide<F, MODE>::value != 0;     // double fast mode
+  constexpr bool FUSED = (MODE == MODE_FAST) && !SLIDE;     // float fast mode
+  typedef StageOps<F, FUSED> S;
+  __shared__ __align__(32) F sdelta[kMaxChunk];
   __shared__ unsigned s_ticket;
 
   if (threadIdx.x == 0)
@@ -760,13 +858,18 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) scan_emit_kernel(const Cha
   const unsigned gblk = rem - j * a.group_blocks;
   const ChunkSpan cs = chunk_span(a.sched, j);
 
-  const F* dsrc = a.delta + (size_t)ch * a.delta_stride + cs.t0;
-  for (unsigned i = threadIdx.x; i < cs.len; i += kEmitWarps * 32) sdelta[i] = dsrc[i];
+  if (a.td_double) chunk_deltas<double, F>(a, ch, cs, sdelta);
+  else chunk_deltas<float, F>(a, ch, cs, sdelta);
+  if (gblk == 0)
+  {
+    if (a.td_double) roll_history<double, F>(a, ch, j);
+    else roll_history<float, F>(a, ch, j);
+  }
   __syncthreads();
 
   const unsigned warp = threadIdx.x >> 5;
   const unsigned lane = threadIdx.x & 31;
-  const unsigned group = gblk * kEmitWarps + warp;
+  const unsigned group = gblk * (blockDim.x >> 5) + warp;
   if (group >= a.groups) return;
 
   const bool last_chunk = (j == a.sched.nchunks - 1);
@@ -786,19 +889,47 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) scan_emit_kernel(const Cha
 
   /* ---- phase A: this chunk's total ---- */
   cx<F> tot[G::CPL];
-  if constexpr (MODE == MODE_FAST)
+  if constexpr (SLIDE)
   {
-    /* total = P_start * sum_i tw^i delta_i, the inner sum by Horner from the chunk's last sample */
+    /* total = P_start * sum_i tw^i delta_i, the inner sum by Horner from the chunk's last sample,
+     * four samples per step once the remaining count is a multiple of four */
     typedef FastOps<F, MODE> X;
 #pragma unroll
     for (int b = 0; b < G::CPL; ++b) tot[b] = zero;
-#pragma unroll 2
-    for (int i = (int)cs.len - 1; i >= 0; --i)
+    int i = (int)cs.len;
+    for (int r = i & 3; r > 0; --r)
     {
-      const F d = sdelta[i];
+      const F d = sdelta[--i];
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b) tot[b] = X::horner(tot[b], L.tw[b], d);
     }
+#if defined(SDFT_B200_HORNER1)
+#pragma unroll 2
+    while (i > 0)
+    {
+      const F d = sdelta[--i];
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b) tot[b] = X::horner(tot[b], L.tw[b], d);
+    }
+#else
+    {
+      cx<F> w2[G::CPL], w3[G::CPL], w4[G::CPL];
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b)
+      {
+        w2[b] = X::cmul(L.tw[b], L.tw[b]);
+        w3[b] = X::cmul(w2[b], L.tw[b]);
+        w4[b] = X::cmul(w2[b], w2[b]);
+      }
+      while (i > 0)
+      {
+        i -= 4;
+        const F d0 = sdelta[i], d1 = sdelta[i + 1], d2 = sdelta[i + 2], d3 = sdelta[i + 3];
+#pragma unroll
+        for (int b = 0; b < G::CPL; ++b) tot[b] = X::horner4(tot[b], L.tw[b], w2[b], w3[b], w4[b], d0, d1, d2, d3);
+      }
+    }
+#endif
 #pragma unroll
     for (int b = 0; b < G::CPL; ++b)
     {
@@ -822,13 +953,13 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) scan_emit_kernel(const Cha
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b)
       {
-        tot[b] = A::mac(tot[b], L.ph[b], d);
+        tot[b] = S::mac(tot[b], L.ph[b], d);
         L.ph[b] = A::rotate(L.ph[b], L.tw[b]);
       }
     }
     const F d = sdelta[body];
 #pragma unroll
-    for (int b = 0; b < G::CPL; ++b) tot[b] = A::mac(tot[b], L.ph[b], d);
+    for (int b = 0; b < G::CPL; ++b) tot[b] = S::mac(tot[b], L.ph[b], d);
   }
 
   /* ---- carry: decoupled look-back with a deterministic, left-to-right summation ----
@@ -951,7 +1082,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) scan_emit_kernel(const Cha
   {
     const size_t row_stride = a.m;
     L.dst = a.out + (size_t)ch * a.out_channel_stride + (size_t)cs.t0 * row_stride + ((long long)e0 - 2);
-    if constexpr (MODE == MODE_FAST)
+    if constexpr (SLIDE)
     {
       /* anchor the demodulated spectrum at the carry (L.ph still holds the chunk's starting phase),
        * then slide; the period's last step needs no special case: conj(tw)^(2m) = 1 */
@@ -975,14 +1106,14 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 4) scan_emit_kernel(const Cha
 #pragma unroll 2
       for (unsigned i = 0; i < body; ++i)
       {
-        L.template step<false>(sdelta[i], (const cx<F>*)nullptr, a.win, row_stride);
+        L.template step<false, FUSED>(sdelta[i], (const cx<F>*)nullptr, a.win, row_stride);
       }
       if (cs.wraps)
       {
         cx<F> restart[G::CPL];
 #pragma unroll
         for (int b = 0; b < G::CPL; ++b) restart[b] = live[b] ? a.f0[e0 + b] : zero;
-        L.template step<true>(sdelta[body], restart, a.win, row_stride);
+        L.template step<true, FUSED>(sdelta[body], restart, a.win, row_stride);
       }
     }
   }

@@ -90,17 +90,22 @@ class SDFT:
         self._f("reset")(self._h)
         self._check()
 
-    def sdft(self, samples):
+    def sdft(self, samples, out=None):
         """Estimate the DFT matrix for the given sample array (sdft.py:76-120).
 
         Returns (samples, bins); for a batch plan the input is (channels, samples) and the result
-        (channels, samples, bins)."""
+        (channels, samples, bins).  `out` (CUDA tensors only) reuses a caller-owned result tensor."""
         if _is_torch_cuda(samples):
             import torch
             x = samples.to(torch.float32 if self.td == "f32" else torch.float64).contiguous()
             n = x.shape[-1]
             shape = (n, self.size) if self.channels == 1 else (self.channels, n, self.size)
-            out = torch.empty(shape, dtype=torch.complex64 if self.fd == "f32" else torch.complex128, device=x.device)
+            fdt = torch.complex64 if self.fd == "f32" else torch.complex128
+            if out is None:
+                out = torch.empty(shape, dtype=fdt, device=x.device)
+            else:
+                assert out.is_cuda and out.is_contiguous() and out.dtype == fdt and out.numel() >= n * self.size * self.channels
+                out = out.view(-1)[: n * self.size * self.channels].view(shape)
             self._use_torch_stream()
             self._f("sdft_batch")(self._h, n, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()))
             self._check()

@@ -1,0 +1,315 @@
+"""
+BASELINE.json configurations 2-5 at FULL size on the GPU, through the C-ABI library.
+
+The CPU oracle cannot produce every row of these matrices (config 2 alone is 64 GiB per window), so it
+walks its state through the signal (`Oracle.advance`, the same arithmetic without the output stage)
+and produces rows only at sampled positions; the GPU result is compared there, plus the final plan
+state and the synthesized samples.  Where even the walk is too long (2^26, 2^30 samples) the oracle
+pins a prefix and size-independent properties pin the rest: shard-count independence, the closed form
+fft(seg * w)[:m] / 2m, reconstruction SNR, state re-seeding.
+
+Tolerances are BASELINE.json's: 1e-9 of full scale for double frequency-domain data, 1e-4 for float.
+"""
+import numpy as np
+import pytest
+
+from sdft_b200 import workloads
+from sdft_b200.shard import time_shards
+
+pytestmark = pytest.mark.gpu
+
+WINDOWS = ("boxcar", "hann", "hamming", "blackman")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    return torch
+
+
+def rel_err(got, want):
+    scale = np.abs(want).max()
+    return np.abs(got - want).max() / (scale if scale > 0 else 1.0)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint8)
+
+
+def _need_bytes(torch, nbytes):
+    free, _ = torch.cuda.mem_get_info()
+    if free < nbytes * 1.05:
+        pytest.skip("needs %.0f GiB of device memory" % (nbytes / 2 ** 30))
+
+
+# --------------------------------------------------------------------------------------------------
+# config 2: 2^20 samples of white noise, m = 4096, double FD, all four windows, one call per window
+# --------------------------------------------------------------------------------------------------
+def test_config2_full_size_all_windows(torch_cuda):
+    torch = torch_cuda
+    from oracle import Oracle
+    from sdft_b200 import SDFT
+    n, m, tile = 1 << 20, 4096, 48
+    _need_bytes(torch, n * m * 16)
+    x = workloads.white_noise(n)
+    xt = torch.from_numpy(x).cuda()
+    out = torch.empty((n, m), dtype=torch.complex128, device="cuda")
+    rng = np.random.default_rng(2)
+    starts = sorted(set([0, 2 * m - tile // 2, 7 * 2 * m + 4071, n // 2 - 7, n - tile]
+                        + [int(s) for s in rng.integers(0, n - tile, 7)]))
+    got_rows, got_y, got_state = {}, {}, {}
+    for w in WINDOWS:
+        g = SDFT(m, w, 1, td="f32", fd="f64")
+        g.sdft(xt, out=out)
+        y = g.isdft(out)
+        torch.cuda.synchronize()
+        got_rows[w] = [out[s:s + tile].cpu().numpy() for s in starts]
+        got_y[w] = y.cpu().numpy()
+        got_state[w] = g.state()
+    del out
+
+    walk = Oracle("f32", "f64", m, "boxcar", 1.0)
+    pos, worst, worst_y = 0, 0.0, 0.0
+    for i, s in enumerate(starts):
+        walk.advance(x[pos:s])
+        pos = s
+        for w in WINDOWS:
+            c = walk.clone(w)
+            want = c.sdft(x[s:s + tile])
+            worst = max(worst, rel_err(got_rows[w][i], want))
+            worst_y = max(worst_y, np.abs(got_y[w][s:s + tile].astype(np.float64) - c.isdft(want)).max())
+    assert worst <= 1e-9, worst
+    assert worst_y <= 2e-6, worst_y
+    walk.advance(x[pos:])
+    co, ho, ao, _ = walk.state()
+    for w in WINDOWS:
+        cg, hg, ag, _ = got_state[w]
+        assert cg == co
+        assert np.array_equal(_bits(hg), _bits(ho))
+        assert rel_err(ag, ao) <= 1e-9
+    # reconstruction SNR (python/examples/latency.py:30-56) is a property of the whole run
+    for w in WINDOWS:
+        assert np.isfinite(workloads.snr_db(x, got_y[w], m - 1))
+    print("config 2: worst row error %.3g of full scale, worst sample error %.3g" % (worst, worst_y))
+
+
+# --------------------------------------------------------------------------------------------------
+# config 3: chirp, m = 2048, float FD, latency 0.5, time-sharded with a 2m-sample halo
+# --------------------------------------------------------------------------------------------------
+def _sharded_roundtrip(SDFT, torch, x_dev, m, world, rows_at=None):
+    """Every shard on a fresh plan primed with its halo (what each rank does); returns y on the host and,
+    for rows_at = {sample: count}, the analysis rows right at those positions."""
+    n = x_dev.numel()
+    ys, rows = [], {}
+    for s in time_shards(n, world, m):
+        if s.size == 0:
+            continue
+        plan = SDFT(m, "hann", 0.5, td="f32", fd="f32")
+        if s.halo:
+            plan.advance(x_dev[s.halo_begin:s.begin])
+        if rows_at and s.begin in rows_at:
+            k = rows_at[s.begin]
+            probe = SDFT(m, "hann", 0.5, td="f32", fd="f32")
+            if s.halo:
+                probe.advance(x_dev[s.halo_begin:s.begin])
+            rows[s.begin] = probe.sdft(x_dev[s.begin:s.begin + k]).cpu().numpy()
+        ys.append(plan.roundtrip(x_dev[s.begin:s.end]))
+    torch.cuda.synchronize()
+    return torch.cat(ys).cpu().numpy(), rows
+
+
+def test_config3_time_shards_match_continuous_reference(torch_cuda):
+    """2^20-sample chirp: the continuous CPU reference run against 1/2/4/8 time shards on the GPU."""
+    torch = torch_cuda
+    from oracle import Oracle
+    from sdft_b200 import SDFT
+    n, m = 1 << 20, 2048
+    delay = int((m - 1) * 0.5)
+    x = workloads.chirp(n)
+    xt = torch.from_numpy(x).cuda()
+    ref = Oracle("f32", "f32", m, "hann", 0.5)
+    y_ref = ref.roundtrip(x)
+    snr_ref = workloads.snr_db(x, y_ref, delay)
+    # rows right after every 8-way shard boundary: where a re-seeded state differs most from the continuous run
+    bounds = [s.begin for s in time_shards(n, 8, m)]
+    walk = Oracle("f32", "f32", m, "hann", 0.5)
+    want_rows, pos = {}, 0
+    for b in bounds:
+        walk.advance(x[pos:b])
+        pos = b
+        want_rows[b] = walk.clone().sdft(x[b:b + 32])
+    scale = max(np.abs(r).max() for r in want_rows.values())
+    for world in (1, 2, 4, 8):
+        y, rows = _sharded_roundtrip(SDFT, torch, xt, m, world, rows_at={b: 32 for b in bounds})
+        assert y.shape == y_ref.shape
+        assert np.abs(y.astype(np.float64) - y_ref).max() <= 1e-3 * np.abs(y_ref).max(), world
+        assert abs(workloads.snr_db(x, y, delay) - snr_ref) < 0.01, world
+        for b, got in rows.items():
+            assert np.abs(got - want_rows[b]).max() / scale <= 1e-4, (world, b)
+
+
+def test_config3_full_size_shard_independence(torch_cuda):
+    """2^26-sample chirp (1 TiB of rows, never materialised): 8 time shards against one continuous GPU
+    run, reconstruction SNR, and halo-seeded rows against the closed form."""
+    torch = torch_cuda
+    from sdft_b200 import SDFT
+    n, m = 1 << 26, 2048
+    delay = int((m - 1) * 0.5)
+    x = workloads.chirp(n)
+    xt = torch.from_numpy(x).cuda()
+    y1, _ = _sharded_roundtrip(SDFT, torch, xt, m, 1)
+    probes = [s.begin for s in time_shards(n, 8, m)][1:]
+    y8, rows = _sharded_roundtrip(SDFT, torch, xt, m, 8, rows_at={b: 1 for b in probes})
+    assert np.abs(y8.astype(np.float64) - y1).max() <= 1e-3 * np.abs(y1).max()
+    s1, s8 = workloads.snr_db(x, y1, delay), workloads.snr_db(x, y8, delay)
+    assert abs(s1 - s8) < 0.01 and s1 > 30.0, (s1, s8)
+    for b, got in rows.items():
+        want = workloads.closed_form_row(x[b + 1 - 2 * m:b + 1], "hann")
+        # float FD carries the reference's own 3e-4 twiddle drift: closed form only to 1e-3
+        assert np.abs(got[0][:m - 1] - want[:m - 1]).max() <= 1e-3 * np.abs(want).max(), b
+    print("config 3: SNR %.2f dB (1 shard) / %.2f dB (8 shards)" % (s1, s8))
+
+
+# --------------------------------------------------------------------------------------------------
+# config 4: independent channels, m = 1024, double FD; one GPU's share (64 of 512 channels x 2^20)
+# --------------------------------------------------------------------------------------------------
+def test_config4_channel_batch_full_size(torch_cuda):
+    torch = torch_cuda
+    from oracle import Oracle
+    from sdft_b200 import SDFT
+    ch, n, m, call, tile = 64, 1 << 20, 1024, 8192, 32
+    _need_bytes(torch, ch * call * m * 16 + ch * n * 8)
+    x = np.stack([workloads.channel_noise(c, n) for c in range(ch)])
+    xt = torch.from_numpy(x).cuda()
+    batch = SDFT(m, "hann", 1, td="f32", fd="f64", channels=ch)
+    out = torch.empty((ch, call, m), dtype=torch.complex128, device="cuda")
+    y = torch.empty((ch, n), dtype=torch.float32, device="cuda")
+    checksum = torch.zeros(ch, dtype=torch.complex128, device="cuda")
+    pinned = (0, 63)
+    sampled_calls = (0, 1, 37, n // call - 1)
+    got_rows = {}
+    for k in range(n // call):
+        batch.sdft(xt[:, k * call:(k + 1) * call].contiguous(), out=out)
+        y[:, k * call:(k + 1) * call] = batch.isdft(out)
+        checksum += out.sum(dim=(1, 2))
+        if k in sampled_calls:
+            for c in pinned:
+                got_rows[(c, k)] = out[c, :tile].cpu().numpy()
+    torch.cuda.synchronize()
+    y = y.cpu().numpy()
+    checksum = checksum.cpu().numpy()
+
+    for c in pinned:
+        walk = Oracle("f32", "f64", m, "hann", 1.0)
+        pos = 0
+        for k in sampled_calls:
+            walk.advance(x[c, pos:k * call])
+            pos = k * call
+            probe = walk.clone()
+            want = probe.sdft(x[c, pos:pos + tile])
+            assert rel_err(got_rows[(c, k)], want) <= 1e-9, (c, k)
+            assert np.abs(y[c, pos:pos + tile] - probe.isdft(want)).max() <= 2e-6
+        walk.advance(x[c, pos:])
+        _, ho, ao, _ = walk.state()
+        cg, hg, ag, _ = batch.state(c)
+        assert np.array_equal(_bits(hg), _bits(ho)) and rel_err(ag, ao) <= 1e-9
+    # the other channels: the batched launch against single-channel plans (another launch geometry)
+    for c in (17, 40):
+        single = SDFT(m, "hann", 1, td="f32", fd="f64")
+        acc = torch.zeros((), dtype=torch.complex128, device="cuda")
+        ys = []
+        for k in range(n // call):
+            d = single.sdft(xt[c, k * call:(k + 1) * call].contiguous(), out=out)
+            ys.append(single.isdft(d))
+            acc += d.sum()
+        torch.cuda.synchronize()
+        assert abs(acc.item() - checksum[c]) <= 1e-9 * abs(checksum[c])
+        assert np.abs(torch.cat(ys).cpu().numpy() - y[c]).max() <= 1e-6
+    snr = [workloads.snr_db(x[c], y[c], m - 1) for c in range(ch)]
+    assert max(snr) - min(snr) < 3.0 and min(snr) > 20.0, (min(snr), max(snr))
+
+
+# --------------------------------------------------------------------------------------------------
+# config 5: endless streaming, 2^30 samples in 4096-sample calls, m = 512, state carried across calls
+# --------------------------------------------------------------------------------------------------
+def _stream_block(torch, begin, count):
+    """workloads.stream evaluated on the device (same formula, int64 arithmetic wraps like uint64)."""
+    def lsr(z, s):
+        return (z >> s) & ((1 << (64 - s)) - 1)
+
+    def c(v):
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    t = torch.arange(begin, begin + count, dtype=torch.int64, device="cuda")
+    z = t + c(0x9E3779B97F4A7C15)
+    z = (z ^ lsr(z, 30)) * c(0xBF58476D1CE4E5B9)
+    z = (z ^ lsr(z, 27)) * c(0x94D049BB133111EB)
+    z = z ^ lsr(z, 31)
+    u = lsr(z, 11).double() * (2.0 / (1 << 53)) - 1.0
+    tone = 0.5 * torch.sin(2 * np.pi * 0.01 * (t % 100).double())
+    return tone + 0.25 * u
+
+
+def test_stream_generator_matches_host_definition(torch_cuda):
+    torch = torch_cuda
+    for begin in (0, 12345, (1 << 30) - 4096):
+        dev = _stream_block(torch, begin, 4096).cpu().numpy()
+        host = workloads.stream(begin, 4096, dtype=np.float64)
+        assert np.abs(dev - host).max() <= 1e-15
+
+
+@pytest.mark.parametrize("td,total_log2,tol", [("f32", 30, 1e-5), ("f64", 27, 1e-9)])
+def test_config5_endless_streaming(torch_cuda, td, total_log2, tol):
+    """State carried across 4096-sample calls.  The CPU oracle walks the first 2^23 samples in lock
+    step (rows at sampled calls, state at the end); the run then continues to 2^30 (f32 time domain;
+    2^27 for the f64 variant) and is checked for drift against the closed form of the last 2m samples
+    and against a fresh plan re-seeded 2m samples before the last call."""
+    torch = torch_cuda
+    from oracle import Oracle
+    from sdft_b200 import SDFT
+    m, call, tile = 512, 4096, 16
+    total, pinned, block = 1 << total_log2, 1 << 23, 1 << 24
+    tdt = torch.float32 if td == "f32" else torch.float64
+    g = SDFT(m, "hann", 1, td=td, fd="f64")
+    out = torch.empty((call, m), dtype=torch.complex128, device="cuda")
+    walk = Oracle(td, "f64", m, "hann", 1.0)
+    sampled = {0, 1, 2, 3, 127, 128, 1000, pinned // call - 1}
+    worst = 0.0
+    last_block = None
+    for b0 in range(0, total, block):
+        xb = _stream_block(torch, b0, block).to(tdt)
+        host = xb[:pinned].cpu().numpy() if b0 == 0 else None
+        pos = 0
+        for k in range(block // call):
+            g.sdft(xb[k * call:(k + 1) * call], out=out)
+            if host is not None and k in sampled:
+                s = k * call
+                walk.advance(host[pos:s])
+                pos = s
+                want = walk.clone().sdft(host[s:s + tile])
+                worst = max(worst, rel_err(out[:tile].cpu().numpy(), want))
+            if host is not None and k == pinned // call - 1:
+                walk.advance(host[pos:])
+                co, ho, ao, _ = walk.state()
+                cg, hg, ag, _ = g.state()
+                assert cg == co and np.array_equal(_bits(hg), _bits(ho))
+                assert rel_err(ag, ao) <= 1e-9
+                host = None
+        last_block = xb
+    torch.cuda.synchronize()
+    g.synchronize()
+    assert worst <= 1e-9, worst
+    last_row = out[-1].cpu().numpy()
+    tail = last_block[-(2 * m + call):].cpu().numpy()
+    # drift against the closed form of the last 2m samples (bins away from the mirror quirk)
+    want = workloads.closed_form_row(tail[-2 * m:].astype(np.float64), "hann")
+    drift = np.abs(last_row[:m - 1] - want[:m - 1]).max() / np.abs(want).max()
+    assert drift <= tol, drift
+    # re-seeded plan: 2m samples of priming end exactly where the last call starts (cursor 0 there)
+    fresh = SDFT(m, "hann", 1, td=td, fd="f64")
+    fresh.advance(tail[:2 * m])
+    again = fresh.sdft(tail[2 * m:])
+    assert rel_err(again, out.cpu().numpy()) <= tol
+    print("config 5 (%s TD): lock-step error %.3g, drift after 2^%d samples %.3g" % (td, worst, total_log2, drift))
