@@ -205,6 +205,80 @@ def run_reference_arm(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+# short device-resident measurements of the other BASELINE configurations' shapes (N = 1 only)
+# ------------------------------------------------------------------------------------------------
+def other_configs(torch, SDFT, scratch, peak):
+    """configs[2..4] are parity-test cases, not bench lines; these are their per-GPU shapes timed briefly
+    (CUDA events, 3 warm-up + 5 timed calls, rows written into the 64 GiB scratch so nothing is L2-resident)."""
+    raw = scratch.view(torch.uint8).view(-1)
+
+    def timed(fn, reps=5):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    def ptr(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    res = {}
+    # config 3 shape: one time shard of the chirp, m = 2048, float FD, latency 0.5
+    m, n = 2048, min(1 << 22, raw.numel() // (2048 * 8))
+    g = SDFT(m, "hann", 0.5, td="f32", fd="f32")
+    g._use_torch_stream()
+    x = torch.rand(n, device=raw.device) * 2 - 1
+    y = torch.empty_like(x)
+    t_a = timed(lambda: g._f("sdft_n")(g._h, n, ptr(x), ptr(raw)))
+    t_s = timed(lambda: g._f("isdft_n")(g._h, n, ptr(raw), ptr(y)))
+    t_r = timed(lambda: g._f("roundtrip_n")(g._h, n, ptr(x), ptr(y)))
+    g._check()
+    res["config3_shard"] = {"workload": "n=%d, m=2048, f32 FD, hann, latency 0.5" % n,
+                            "analysis_bin_updates_per_s": n * m / t_a, "analysis_GBps": n * m * 8 / t_a / 1e9,
+                            "analysis_frac_of_hbm_peak": n * m * 8 / t_a / 1e9 / peak,
+                            "synthesis_samples_per_s": n / t_s, "synthesis_GBps": n * m * 8 / t_s / 1e9,
+                            "fused_roundtrip_bin_updates_per_s": n * m / t_r, "fused_roundtrip_samples_per_s": n / t_r}
+    # config 4 shape: 64 channels per GPU, m = 1024, double FD
+    m, ch = 1024, 64
+    n = min(1 << 16, raw.numel() // (ch * m * 16))
+    g = SDFT(m, "hann", 1, td="f32", fd="f64", channels=ch)
+    g._use_torch_stream()
+    x = torch.rand(ch * n, device=raw.device) * 2 - 1
+    y = torch.empty_like(x)
+    t_a = timed(lambda: g._f("sdft_batch")(g._h, n, ptr(x), ptr(raw)))
+    t_r = timed(lambda: g._f("roundtrip_n")(g._h, n, ptr(x), ptr(y)))
+    g._check()
+    res["config4_per_gpu"] = {"workload": "64 channels x %d samples per call, m=1024, f64 FD, hann, one launch" % n,
+                              "analysis_bin_updates_per_s": ch * n * m / t_a, "analysis_GBps": ch * n * m * 16 / t_a / 1e9,
+                              "analysis_frac_of_hbm_peak": ch * n * m * 16 / t_a / 1e9 / peak,
+                              "fused_roundtrip_bin_updates_per_s": ch * n * m / t_r}
+    # config 5 shape: endless streaming in 4096-sample calls, m = 512, state carried across calls
+    m, n, calls = 512, 4096, 1024
+    g = SDFT(m, "hann", 1, td="f32", fd="f64")
+    g._use_torch_stream()
+    x = torch.rand(calls * n, device=raw.device) * 2 - 1
+    tile = n * m * 16
+    xs = [ctypes.c_void_p(x.data_ptr() + c * n * 4) for c in range(calls)]
+    os_ = [ctypes.c_void_p(raw.data_ptr() + c * tile) for c in range(calls)]
+    f = g._f("sdft_n")
+
+    def stream_calls():
+        for c in range(calls):
+            f(g._h, n, xs[c], os_[c])
+    t_c = timed(stream_calls, reps=3) / calls
+    g._check()
+    res["config5_stream"] = {"workload": "%d back-to-back calls of 4096 samples on one plan, m=512, f64 FD, hann; "
+                                         "rows into %d distinct 32 MiB tiles" % (calls, calls),
+                             "us_per_call": t_c * 1e6, "analysis_bin_updates_per_s": n * m / t_c,
+                             "analysis_GBps": n * m * 16 / t_c / 1e9, "analysis_frac_of_hbm_peak": n * m * 16 / t_c / 1e9 / peak}
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 def run_b200_arm(args, rank, local_rank, world):
@@ -319,7 +393,11 @@ def run_b200_arm(args, rank, local_rank, world):
              "ms_per_step": t_synth / args.steps * 1e3,
              "roofline": {"bound": "hbm", "achieved": args.steps * alg_bytes / t_synth / 1e9, "peak": peak,
                           "unit": "GB/s", "frac": args.steps * alg_bytes / t_synth / 1e9 / peak}}
-    del out, y
+    del y
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = other_configs(torch, SDFT, out, peak)
+    del out
     torch.cuda.empty_cache()
 
     # ---- e2e: C-ABI call with host buffers (pinned), copies inside the timed region ---------------
@@ -349,7 +427,7 @@ def run_b200_arm(args, rank, local_rank, world):
 
     # the reference's own usage pattern (test/test.c:79-80): analysis then synthesis, hop by hop, with only
     # SAMPLES crossing PCIe (host in, host out) and the rows living in a device tile
-    n_rt = min(1 << 18, n)
+    n_rt = min(1 << 20, n)
     xr = torch.from_numpy(x_host[:n_rt].copy()).pin_memory()
     yr = torch.empty(n_rt, dtype=torch.float32).pin_memory()
     pr = SDFT(m, "hann", 1, td="f32", fd="f64")
@@ -371,7 +449,7 @@ def run_b200_arm(args, rank, local_rank, world):
                         "samples_per_s": world * args.steps * n_rt / t_rt,
                         "h2d_bytes_per_step": n_rt * 4, "d2h_bytes_per_step": n_rt * 4,
                         "sample": "sdft_b200_f32f64_roundtrip_n(host samples -> host samples), n=%d, m=%d, hann: "
-                                  "analysis + synthesis, rows stay in a device tile" % (n_rt, m)}
+                                  "analysis + synthesis fused in one kernel, the rows never reach memory" % (n_rt, m)}
 
     # ---- CPU baseline beside it (rank 0, N = 1) -----------------------------------------------------
     cpu = None
@@ -392,6 +470,7 @@ def run_b200_arm(args, rank, local_rank, world):
                        "n_samples": n, "m": m, "windows": list(WINDOWS), "parallelism": "channel-sharded x%d" % world,
                        "l2": "no flush: each window writes %.0f GiB (>> 126 MB L2)" % (n * m * 16 / 2 ** 30)},
             "roofline": roofline, "synthesis": synth, "e2e": e2e, "cpu_baseline": cpu, "clocks": clk,
+            "other_configs": extras,
             "gpu_launches": int(launches),
         }
         print(json.dumps(line), flush=True)
@@ -408,6 +487,7 @@ def main():
     ap.add_argument("--n", type=int, default=N_SAMPLES, help="samples per window (default 2^20)")
     ap.add_argument("--e2e-n", type=int, default=1 << 16, help="samples per e2e step (host buffers)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short measurements of configs 3-5")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

@@ -79,7 +79,7 @@ struct sdft_b200_plan
   int acc_sel = 0;
   void* phase_scratch = nullptr;   // cells complex values, introspection only
 
-  Buffer samples, synth_out, tile[2];
+  Buffer samples, synth_out, tile[2], part;
   Buffer prefix, chain_totals, flags;   // chained scan: inclusive prefixes, chunk totals, epoch-stamped flags
   unsigned* control = nullptr;   // [0] work ticket, [1] spin-wait timeout flag
   unsigned epoch = 0;
@@ -324,7 +324,7 @@ void plan_destroy(Plan* p)
   if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
   void* ptrs[] = { p->tw_ext, p->tws, p->f0, p->history[0], p->history[1], p->acc_state[0], p->acc_state[1], p->phase_scratch,
                    p->prefix.ptr, p->chain_totals.ptr, p->flags.ptr, p->control,
-                   p->samples.ptr, p->synth_out.ptr, p->tile[0].ptr, p->tile[1].ptr };
+                   p->samples.ptr, p->synth_out.ptr, p->part.ptr, p->tile[0].ptr, p->tile[1].ptr };
   for (void* q : ptrs)
     if (q) cudaFree(q);
   for (int w = 0; w < 2; ++w)
@@ -370,7 +370,7 @@ Plan* plan_create(size_t m, int window, double latency, size_t channels)
   p->tile_bytes = env_size("SDFT_B200_TILE_MB", 128) << 20;
   p->forced_chunk = env_size("SDFT_B200_CHUNK", 0);
   p->forced_warps = (unsigned)env_size("SDFT_B200_WARPS", 0);
-  if (p->forced_warps > (unsigned)kEmitWarps) p->forced_warps = kEmitWarps;
+  if (p->forced_warps > (unsigned)kScanWarps) p->forced_warps = kScanWarps;
   {
     /* double frequency domain: fast (demodulated replay) unless SDFT_B200_F64=modulated.
      * float: the reference's modulated scheme, every rounding kept (rows are bit-exact within a chunk).
@@ -458,22 +458,26 @@ unsigned choose_chunk(const Plan* p, size_t n)
     if (c > (size_t)kMaxChunk) c = kMaxChunk;
     return (unsigned)c;
   }
-  /* enough warps to fill 148 SMs x 16 resident warps a few times over, else the shortest chunk */
-  const double want = 148.0 * 16.0 * 4.0;
-  const double per_sample = (double)groups_for(p) * (double)p->channels;
-  unsigned c = kAutoChunk;
-  while (c > (unsigned)kF0Stride && ((double)n / c) * per_sample < want) c >>= 1;
-  return c;
+  /* Measured on B200 (tools/chunk_sweep.py, profiles/r01_chunk_sweep.md): the best chunk length is a
+   * function of the call's total warp-steps U = samples x groups x channels.  Short chunks expose the
+   * per-chunk latencies (ticket, table loads, look-back), long chunks leave SMs without work. */
+  const double u = (double)n * (double)groups_for(p) * (double)p->channels;
+  if (u < 16384.0) return 32;
+  if (u < 100.0e3) return 64;
+  if (u < 4.0e6) return 128;
+  if (u < 16.0e6) return 256;
+  return kAutoChunk;
 }
 
-template <typename F, bool EMIT>
+template <typename F, int EMIT>
 void launch_chain(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps)
 {
   const dim3 grid(a.total_blocks);
+  const size_t smem = scan_smem_bytes<F>(warps, a.sched.chunk);
 #define SDFT_CHAIN_CASE(W, MODE)                                                                       \
   case W:                                                                                              \
-    if (vec) scan_emit_kernel<F, W, true, EMIT, MODE><<<grid, warps * 32, 0, p->stream>>>(a);          \
-    else scan_emit_kernel<F, W, false, EMIT, MODE><<<grid, warps * 32, 0, p->stream>>>(a);             \
+    if (vec) scan_emit_kernel<F, W, true, EMIT, MODE><<<grid, warps * 32, smem, p->stream>>>(a);       \
+    else scan_emit_kernel<F, W, false, EMIT, MODE><<<grid, warps * 32, smem, p->stream>>>(a);          \
     break;
   if (p->mode == MODE_FAST)
   {
@@ -499,33 +503,32 @@ void launch_chain(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps)
   p->launches++;
 }
 
-/* warps per scan/emit CTA: the widest CTA (<= kEmitWarps) that leaves the fewest idle warp slots in
- * the last CTA of a chunk (34 groups -> 2 warps, 17 -> 1, 32 -> 4) */
-unsigned emit_warps_for(unsigned groups)
+/* warps (= consecutive chunks) per scan/emit CTA */
+unsigned scan_warps_for(const Plan* p, unsigned chunk, unsigned nchunks)
 {
-  unsigned best = 1, best_waste = 0;
-  for (unsigned w = 2; w <= (unsigned)kEmitWarps; ++w)
-  {
-    const unsigned waste = ((groups + w - 1) / w) * w - groups;
-    if (waste <= best_waste) { best = w; best_waste = waste; }
-  }
-  return best;
+  /* 4 is the measured optimum: wider CTAs shorten the global chain further but pile their stores onto
+   * one SM, narrower ones lengthen the chain */
+  unsigned w = p->forced_warps ? p->forced_warps : 4u;
+  if (w > (unsigned)kSmemSamples / chunk) w = (unsigned)kSmemSamples / chunk;
+  if (w > (unsigned)kScanWarps) w = kScanWarps;
+  if (w > nchunks) w = nchunks;
+  if (w < 1) w = 1;
+  return w;
 }
 
 /* production path: the single-pass chained scan/emit kernel (deltas and history are its prologue) */
 template <typename T, typename F>
-bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride)
+bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride, F* part = nullptr)
 {
   const unsigned m = (unsigned)p->m;
   const unsigned ch = (unsigned)p->channels;
   const unsigned chunk = choose_chunk(p, n);
   const Schedule sched = make_schedule(p->cursor, n, m, chunk);
   const unsigned groups = groups_for(p);
-  const unsigned warps = p->forced_warps ? p->forced_warps : emit_warps_for(groups);
-  const unsigned group_blocks = (groups + warps - 1) / warps;
-  const size_t items = (size_t)ch * sched.nchunks * groups;
-  const size_t blocks = (size_t)ch * sched.nchunks * group_blocks;
-  if (blocks >= (1ull << 31))
+  const unsigned warps = scan_warps_for(p, chunk, sched.nchunks);
+  const unsigned nblocks = (sched.nchunks + warps - 1) / warps;
+  const size_t items = (size_t)ch * nblocks * groups;
+  if (items >= (1ull << 31))
   {
     plan_fail(p, SDFT_B200_ERR_ARG, "analysis: call too large for one launch", __FILE__, __LINE__);
     return false;
@@ -559,24 +562,34 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   a.flags = (unsigned*)p->flags.ptr;
   a.control = p->control;
   a.epoch = p->epoch;
-  a.total_blocks = (unsigned)blocks;
+  a.total_blocks = (unsigned)items;
+  a.nblocks = nblocks;
+  a.channels = ch;
   a.m = m;
   a.cells = (unsigned)p->cells;
   a.out = out;
   a.out_channel_stride = out_stride;
+  a.tws = (const cx<F>*)p->tws;
+  a.part = part;
   a.groups = groups;
-  a.group_blocks = group_blocks;
   a.win = make_window_const<F>(p->m, p->window);   // sdft.h:422, :371
-  if (out)
+  if (part)
+  {
+    prof_mark(p, 0);
+    if (p->latency == 1) launch_chain<F, EMIT_SYNTH_UNIT>(p, a, false, warps);   // exact compare, sdft.h:639
+    else launch_chain<F, EMIT_SYNTH>(p, a, false, warps);
+    prof_mark(p, 0);
+  }
+  else if (out)
   {
     const bool vec = can_vectorize<F>(m, out, out_stride);
     prof_mark(p, 0);
-    launch_chain<F, true>(p, a, vec, warps);
+    launch_chain<F, EMIT_ROWS>(p, a, vec, warps);
     prof_mark(p, 0);
   }
   else
   {
-    launch_chain<F, false>(p, a, false, warps);
+    launch_chain<F, EMIT_NONE>(p, a, false, warps);
   }
   CU_TRY(p, cudaGetLastError());
   p->hist_sel ^= 1;
@@ -831,7 +844,9 @@ bool do_isdft_nd(Plan* p, size_t n, const cx<F>** rows_in, T* samples)
   return true;
 }
 
-/* analysis -> synthesis without handing the matrix to the caller: rows live only in a device tile */
+/* analysis -> synthesis in ONE kernel: the rows never exist in memory.  Every warp weighs and reduces
+ * its bins per time step (SynthLane), per-group partial sums go to a scratch buffer and a small second
+ * kernel adds the groups in order.  Long calls are cut into pieces that bound the scratch. */
 template <typename T, typename F>
 bool do_roundtrip(Plan* p, size_t n, const T* in, T* out)
 {
@@ -840,9 +855,8 @@ bool do_roundtrip(Plan* p, size_t n, const T* in, T* out)
   bool ok = true;
   const T* x = stage_samples<T>(p, n, in, &ok);
   if (!ok) return false;
-  const size_t m = p->m, ch = p->channels, row_bytes = m * sizeof(cx<F>);
-  const size_t rows = tile_rows(p, n, row_bytes);
-  if (!reserve(p, p->tile[0], ch * rows * row_bytes)) return false;
+  const size_t ch = p->channels;
+  const unsigned groups = groups_for(p);
   const bool out_dev = classify(out) == kDevice;
   T* y = out;
   if (!out_dev)
@@ -850,11 +864,19 @@ bool do_roundtrip(Plan* p, size_t n, const T* in, T* out)
     if (!reserve(p, p->synth_out, ch * n * sizeof(T))) return false;
     y = (T*)p->synth_out.ptr;
   }
-  for (size_t t0 = 0; t0 < n; t0 += rows)
+  size_t piece = env_size("SDFT_B200_ROUNDTRIP_PIECE", (size_t)1 << 22);
+  if (piece > n) piece = n;
+  if (!reserve(p, p->part, ch * groups * piece * sizeof(F))) return false;
+  for (size_t t0 = 0; t0 < n; t0 += piece)
   {
-    const size_t len = (t0 + rows <= n) ? rows : n - t0;
-    if (!analysis_device<T, F>(p, len, x + t0, n, (cx<F>*)p->tile[0].ptr, len * m)) return false;
-    if (!synthesis_device<T, F>(p, len, (const cx<F>*)p->tile[0].ptr, len * m, y + t0, n)) return false;
+    const size_t len = (t0 + piece <= n) ? piece : n - t0;
+    if (!analysis_chained<T, F>(p, len, x + t0, n, (cx<F>*)nullptr, 0, (F*)p->part.ptr)) return false;
+    size_t blocks = (len + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    synth_finish_kernel<T, F><<<dim3((unsigned)blocks, (unsigned)ch), 256, 0, p->stream>>>(
+        (const F*)p->part.ptr, groups, len, y + t0, n);
+    p->launches++;
+    CU_TRY(p, cudaGetLastError());
   }
   if (!out_dev)
   {

@@ -40,10 +40,6 @@ namespace sdftb200
 constexpr int kF0Stride = 32;     // phase table holds P at every 32nd cursor
 constexpr int kMaxChunk = 1024;   // longest chunk the kernels accept (samples)
 constexpr int kAutoChunk = 512;   // longest chunk the heuristic picks (measured best on B200)
-constexpr int kEmitWarps = 4;     // most warps per scan/emit CTA (the launch picks 1..4, see emit_warps_for)
-#ifndef SDFT_B200_MINBLOCKS
-#define SDFT_B200_MINBLOCKS 4     // resident 128-thread CTAs per SM the register allocation must allow
-#endif
 
 template <typename F> struct cx { F r, i; };
 
@@ -582,8 +578,41 @@ struct EmitLane
   }
 
   /* one time step; RESTART = the period's last step, after which the phase restarts (sdft.h:566-576) */
+  __device__ __forceinline__ void store_rows(const cx<F>* y, size_t row_stride)
+  {
+    if (VEC)
+    {
+#pragma unroll
+      for (int g = 0; g < G::NGROUP; ++g)
+        if (ok[g * G::GROUP]) store_group(dst + g * G::GROUP, y + g * G::GROUP);
+    }
+    else
+    {
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b)
+        if (ok[b]) store_one(dst + b, y[b]);
+    }
+    dst += row_stride;
+  }
+
   template <bool RESTART, bool FUSED>
   __device__ __forceinline__ void step(F d, const cx<F>* restart, const WindowConst<F>& win, size_t row_stride)
+  {
+    cx<F> y[G::CPL];
+    compute<RESTART, FUSED>(d, restart, win, y);
+    store_rows(y, row_stride);
+  }
+
+  __device__ __forceinline__ void fast_step(F d, const WindowConst<F>& win, size_t row_stride)
+  {
+    cx<F> y[G::CPL];
+    fast_compute(d, win, y);
+    store_rows(y, row_stride);
+  }
+
+  /* one time step of the modulated replay: windowed spectrum of this lane's cells into y[] */
+  template <bool RESTART, bool FUSED>
+  __device__ __forceinline__ void compute(F d, const cx<F>* restart, const WindowConst<F>& win, cx<F>* y)
   {
     typedef Arith<F> A;
     typedef StageOps<F, FUSED> S;
@@ -595,7 +624,6 @@ struct EmitLane
       ph[b] = RESTART ? restart[b] : A::rotate(ph[b], tw[b]);
       x[b] = S::demod(acc[b], ph[b]);
     }
-    cx<F> y[G::CPL];
     if (WINDOW == 0)
     {
 #pragma unroll
@@ -622,28 +650,14 @@ struct EmitLane
         y[b] = S::template window<WINDOW>(m2, m1, x[b], p1, p2, win);
       }
     }
-    if (VEC)
-    {
-#pragma unroll
-      for (int g = 0; g < G::NGROUP; ++g)
-        if (ok[g * G::GROUP]) store_group(dst + g * G::GROUP, y + g * G::GROUP);
-    }
-    else
-    {
-#pragma unroll
-      for (int b = 0; b < G::CPL; ++b)
-        if (ok[b]) store_one(dst + b, y[b]);
-    }
-    dst += row_stride;
   }
 
   /* fast mode (double): acc[] holds the DEMODULATED spectrum, tw[] holds conj(tw); ph[] is unused */
-  __device__ __forceinline__ void fast_step(F d, const WindowConst<F>& win, size_t row_stride)
+  __device__ __forceinline__ void fast_compute(F d, const WindowConst<F>& win, cx<F>* y)
   {
     typedef Arith<F> A;
 #pragma unroll
     for (int b = 0; b < G::CPL; ++b) acc[b] = A::slide(acc[b], tw[b], d);
-    cx<F> y[G::CPL];
     if (WINDOW == 0)
     {
 #pragma unroll
@@ -669,43 +683,151 @@ struct EmitLane
         y[b] = A::template fast_window<WINDOW>(m2, m1, acc[b], p1, p2, win);
       }
     }
-    if (VEC)
-    {
-#pragma unroll
-      for (int g = 0; g < G::NGROUP; ++g)
-        if (ok[g * G::GROUP]) store_group(dst + g * G::GROUP, y + g * G::GROUP);
-    }
-    else
-    {
-#pragma unroll
-      for (int b = 0; b < G::CPL; ++b)
-        if (ok[b]) store_one(dst + b, y[b]);
-    }
-    dst += row_stride;
   }
 };
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused synthesis (EMIT_SYNTH): instead of storing the rows, every lane weighs its bins as sdft_isdft
+ * does (sdft.h:639-652: (-1)^k Re(dft[k]) for latency 1, Re(dft[k] * tws[k]) otherwise) and the warp
+ * reduces eight time steps at once with a transposing butterfly (9 shuffles per 8 steps instead of 5
+ * per step): after three exchange rounds every lane holds ONE step's sum over eight lanes, two plain
+ * butterfly rounds finish it.  The warp's partial sums over its bins go to part[group][t]; a second
+ * tiny kernel adds the groups in order and scales by 2 (sdft.h:654-656).  Fixed order: deterministic.
+ * ---------------------------------------------------------------------------------------------- */
+template <typename F, int CPL, bool UNIT>
+struct SynthLane
+{
+  F wr[CPL], wi[CPL];   // weights of this lane's bins; 0 for halo / out-of-range cells
+  F p[8];
+
+  __device__ __forceinline__ void setup(const cx<F>* __restrict__ tws, int e0, const bool* ok)
+  {
+#pragma unroll
+    for (int b = 0; b < CPL; ++b)
+    {
+      const int k = e0 + b - 2;
+      if (UNIT)
+      {
+        wr[b] = ok[b] ? ((k & 1) ? (F)(-1) : (F)(1)) : (F)0;
+        wi[b] = (F)0;
+      }
+      else
+      {
+        wr[b] = ok[b] ? tws[k].r : (F)0;
+        wi[b] = ok[b] ? tws[k].i : (F)0;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = (F)0;
+  }
+
+  __device__ __forceinline__ F weigh(const cx<F>* y) const
+  {
+    F s = (F)0;
+#pragma unroll
+    for (int b = 0; b < CPL; ++b)
+    {
+      s = fma(y[b].r, wr[b], s);
+      if (!UNIT) s = fma(-y[b].i, wi[b], s);
+    }
+    return s;
+  }
+
+  /* sums p[0..7] over the warp; lane (4 q) returns the total of step q's slot, see step_of() */
+  __device__ __forceinline__ F reduce8(unsigned lane)
+  {
+    F a[4], b2[2], c;
+    {
+      const bool hi = (lane & 16) != 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+      {
+        const F keep = hi ? p[4 + i] : p[i];
+        const F give = hi ? p[i] : p[4 + i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+      }
+    }
+    {
+      const bool hi = (lane & 8) != 0;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+      {
+        const F keep = hi ? a[2 + i] : a[i];
+        const F give = hi ? a[i] : a[2 + i];
+        b2[i] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+      }
+    }
+    {
+      const bool hi = (lane & 4) != 0;
+      const F keep = hi ? b2[1] : b2[0];
+      const F give = hi ? b2[0] : b2[1];
+      c = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+    }
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = (F)0;
+    return c;
+  }
+  /* which of the eight steps lane `lane` holds after reduce8 */
+  static __device__ __forceinline__ unsigned step_of(unsigned lane)
+  {
+    return ((lane >> 4) & 1u) * 4u + ((lane >> 3) & 1u) * 2u + ((lane >> 2) & 1u);
+  }
+};
+
+/* part: (channels, groups, n) partial sums -> samples (channels, sample_stride), sdft.h:654-656 */
+template <typename T, typename F>
+__global__ void synth_finish_kernel(const F* __restrict__ part, unsigned groups, unsigned long long n,
+                                    T* __restrict__ samples, size_t sample_stride)
+{
+  const unsigned ch = blockIdx.y;
+  const F* base = part + (size_t)ch * groups * n;
+  T* y = samples + (size_t)ch * sample_stride;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+  {
+    F s = (F)0;
+    for (unsigned g = 0; g < groups; ++g) s += base[(size_t)g * n + t];
+    y[t] = (T)(s * (F)2);
+  }
+}
 
 
 /* ------------------------------------------------------------------------------------------------
  * K23  single-pass chained scan + emit (the production analysis kernel)
  *
- *      Same work items as K3 (one warp = one chunk x 128 cells), but the warp first computes its own
- *      chunk total (K2's job, FP64/FP32 only, no memory traffic), then obtains the carry from the warp
- *      that owns the PREVIOUS chunk of the same cells, publishes its inclusive prefix, and only then
- *      replays the chunk and streams the rows out.  Warps in the compute phase and warps in the store
- *      phase share every SM, so the scan arithmetic hides under the HBM-bound stores instead of
- *      running as separate kernels in front of them.
+ *      Work decomposition.  Time is cut into chunks (make_schedule), bins into warp-wide groups of
+ *      Geo<F>::WC cells.  One WARP owns one (chunk, group); one CTA owns `W` CONSECUTIVE CHUNKS of the
+ *      same group of one channel (a "block item").  Per warp:
+ *        A. the chunk's own total  sum_i P[c+i] delta_i  (FP only, no memory traffic);
+ *        B. the carry: totals of the CTA's chunks meet in shared memory; warp 0 adds them up in chunk
+ *           order, publishes the CTA's aggregate, obtains the carry at the CTA's first chunk by a
+ *           decoupled look-back over the PRECEDING CTAs of the same chain and publishes the inclusive
+ *           prefix; every warp then adds the totals of the chunks before its own (shared memory again).
+ *           The global chain is therefore W times shorter than the chunk chain, which is what bounds the
+ *           latency of short calls (streaming, host tiles);
+ *        C. replay the chunk from the carry, window across neighbouring cells, stream the rows out.
+ *      Warps in phase A (FP only) and warps in phase C (store-bound) share every SM, so the scan
+ *      arithmetic hides under the HBM-bound stores.
  *
- *      Ordering.  carry_j = (((acc + total_0) + total_1) + ...) + total_{j-1}, always added in chunk
- *      order, so results are deterministic and independent of timing (see the look-back comment in the
- *      kernel).  Work items are handed out through an atomic ticket in (channel, chunk, group) order;
- *      an item only ever waits for items with smaller tickets, which have all started and publish
- *      their totals without waiting for anybody, so the kernel cannot deadlock whatever the block
- *      scheduler does.  Publication: cells are written by all lanes, fenced, then lane 0 releases a
- *      per-item flag stamped with the call's epoch (no flag clearing between calls); consumers acquire
- *      the flag and read the cells through L2.  A wait that exceeds kSpinLimitNs sets *error and gives
- *      up, so a logic error shows up as a reported failure, not as a hung device.
+ *      Ordering.  Every sum is taken in a fixed order that depends on the launch geometry only:
+ *      carry(first chunk of CTA b) = ((acc + A_0) + A_1) + ... + A_{b-1} with A_c the CTA aggregates
+ *      (each the in-order sum of its chunk totals), then + the totals of the CTA's earlier chunks in
+ *      order.  The look-back walks back to the nearest CTA whose inclusive PREFIX is already published
+ *      and adds the aggregates after it from left to right -- the same additions whatever that CTA
+ *      happens to be, so results do not depend on timing.  Block items are handed out through an
+ *      atomic ticket in (block, channel, group) order; an item only ever waits for items with smaller
+ *      tickets, which have all started and publish their aggregates without waiting for anybody, so
+ *      the kernel cannot deadlock whatever the block scheduler does.  Publication: cells are written
+ *      by all lanes, fenced, then lane 0 releases a per-item flag stamped with the call's epoch (no
+ *      flag clearing between calls); consumers acquire the flag and read the cells through L2.  A wait
+ *      that exceeds kSpinLimitNs sets *error and gives up, so a logic error shows up as a reported
+ *      failure, not as a hung device.
  * ---------------------------------------------------------------------------------------------- */
+constexpr int kScanWarps = 8;          // most warps (= consecutive chunks) per scan/emit CTA
+constexpr int kSmemSamples = 2048;     // deltas held per CTA: W * chunk length <= kSmemSamples
+
 template <typename F> struct ChainArgs
 {
   Schedule sched;
@@ -719,18 +841,21 @@ template <typename F> struct ChainArgs
   const cx<F>* f0;         // (rows, cells)
   const cx<F>* acc_in;     // (channels, cells)
   cx<F>* acc_out;
-  cx<F>* totals;           // (channels, nchunks, groups, Geo<F>::WC) each chunk's own total
-  cx<F>* prefix;           // (channels, nchunks, groups, Geo<F>::WC) inclusive prefix after each chunk
-  unsigned* flags;         // (channels, nchunks, groups): 2*epoch = total published, 2*epoch+1 = prefix published
+  cx<F>* totals;           // (channels, nblocks, groups, Geo<F>::WC) aggregate of each block item
+  cx<F>* prefix;           // (channels, nblocks, groups, Geo<F>::WC) inclusive prefix after each block item
+  unsigned* flags;         // (channels, nblocks, groups): 2*epoch = aggregate published, 2*epoch+1 = prefix published
   unsigned* control;       // [0] ticket counter, [1] error flag
   unsigned epoch;
-  unsigned total_blocks;
+  unsigned total_blocks;   // nblocks * channels * groups
+  unsigned nblocks;        // block items per chain: ceil(nchunks / warps per CTA)
+  unsigned channels;
   unsigned m;
   unsigned cells;
   cx<F>* out;              // (channels, n, m) or nullptr
   size_t out_channel_stride;
+  const cx<F>* tws;        // (m) synthesis twiddles, EMIT_SYNTH only
+  F* part;                 // (channels, groups, n) per-group partial sums of the fused synthesis
   unsigned groups;
-  unsigned group_blocks;
   WindowConst<F> win;
 };
 
@@ -774,8 +899,11 @@ template <> __device__ __forceinline__ void store_l2<float>(cx<float>* p, cx<flo
 }
 
 enum { MODE_MODULATED = 0, MODE_FAST = 1 };
+/* what phase C does with the windowed spectrum: nothing (state update only), store the (n, m) rows, or
+ * feed the fused synthesis (latency == 1 / any latency, sdft.h:639) */
+enum { EMIT_NONE = 0, EMIT_ROWS = 1, EMIT_SYNTH_UNIT = 2, EMIT_SYNTH = 3 };
 
-/* float never runs the fast mode; these keep the shared kernel body compilable */
+/* float never runs the demodulated replay; these keep the shared kernel body compilable */
 template <typename F, int MODE> struct FastOps
 {
   static __device__ __forceinline__ cx<F> horner(cx<F> h, cx<F>, F) { return h; }
@@ -795,16 +923,16 @@ template <> struct FastOps<double, MODE_FAST>
   static __device__ __forceinline__ cx<F> demod(cx<F> a, cx<F> p) { return Arith<F>::demod(a, p); }
 };
 
-/* K1 (fused prologue)  deltas of one chunk in TIME-DOMAIN precision (sdft.h:564, :186-191):
- *     ext(t) = history[t] for t < 2m, samples[t - 2m] otherwise; delta[t] = ext(t + 2m) - ext(t),
- *     one rounding in T, then widened to F. */
+/* K1 (fused prologue)  deltas of one chunk in TIME-DOMAIN precision (sdft.h:564, :186-191), loaded by
+ *     the warp that owns the chunk:  ext(t) = history[t] for t < 2m, samples[t - 2m] otherwise;
+ *     delta[t] = ext(t + 2m) - ext(t), one rounding in T, then widened to F. */
 template <typename T, typename F>
-__device__ __forceinline__ void chunk_deltas(const ChainArgs<F>& a, unsigned ch, const ChunkSpan& cs, F* sdelta)
+__device__ __forceinline__ void chunk_deltas(const ChainArgs<F>& a, unsigned ch, const ChunkSpan& cs, F* sdelta, unsigned lane)
 {
   const unsigned period = a.sched.period;
   const T* x = (const T*)a.samples + (size_t)ch * a.sample_stride;
   const T* ho = (const T*)a.hist_old + (size_t)ch * period;
-  for (unsigned i = threadIdx.x; i < cs.len; i += blockDim.x)
+  for (unsigned i = lane; i < cs.len; i += 32)
   {
     const unsigned long long t = cs.t0 + i;
     const T newest = x[t];
@@ -813,15 +941,15 @@ __device__ __forceinline__ void chunk_deltas(const ChainArgs<F>& a, unsigned ch,
     sdelta[i] = (F)diff * a.scale;
   }
 }
-/* the history the next call starts from; entries are dealt out over the chunks of the call */
+/* the history the next call starts from; entries are dealt out over the block items of group 0 */
 template <typename T, typename F>
-__device__ __forceinline__ void roll_history(const ChainArgs<F>& a, unsigned ch, unsigned j)
+__device__ __forceinline__ void roll_history(const ChainArgs<F>& a, unsigned ch, unsigned jb)
 {
   const unsigned period = a.sched.period;
   const T* x = (const T*)a.samples + (size_t)ch * a.sample_stride;
   const T* ho = (const T*)a.hist_old + (size_t)ch * period;
   T* hn = (T*)a.hist_new + (size_t)ch * period;
-  for (unsigned i = j * blockDim.x + threadIdx.x; i < period; i += a.sched.nchunks * blockDim.x)
+  for (unsigned i = jb * blockDim.x + threadIdx.x; i < period; i += a.nblocks * blockDim.x)
   {
     const unsigned long long pos = a.sched.n + i;   // position inside history || samples
     hn[i] = (pos < period) ? ho[pos] : x[pos - period];
@@ -832,16 +960,99 @@ __device__ __forceinline__ void roll_history(const ChainArgs<F>& a, unsigned ch,
 template <typename F, int MODE> struct IsSlide { enum { value = 0 }; };
 template <> struct IsSlide<double, MODE_FAST> { enum { value = 1 }; };
 
-template <typename F, int WINDOW, bool VEC, bool EMIT, int MODE>
-__global__ void __launch_bounds__(kEmitWarps * 32, SDFT_B200_MINBLOCKS) scan_emit_kernel(const ChainArgs<F> a)
+/* carry at the first chunk of block item `jb` (jb > 0): decoupled look-back over the preceding block
+ * items of the chain, deterministic left-to-right summation (one warp; see the header comment) */
+template <typename F>
+__device__ __forceinline__ void look_back(const ChainArgs<F>& a, size_t item, size_t item_stride, unsigned jb, unsigned lane,
+                                          cx<F>* acc)
+{
+  typedef Geo<F> G;
+  typedef Arith<F> A;
+  const unsigned code_total = a.epoch * 2u, code_prefix = a.epoch * 2u + 1u;
+  long long top = (long long)jb - 1;
+  long long q = -1;
+  unsigned long long t_start = 0;
+  while (true)
+  {
+    const long long idx = top - (long long)lane;
+    unsigned f = 0;
+    if (idx >= 0) f = ld_acquire_u32(a.flags + (item - (size_t)(jb - idx) * item_stride));
+    const bool is_prefix = (idx >= 0) && (f == code_prefix);
+    const bool is_none = (idx >= 0) && (f != code_prefix) && (f != code_total);
+    const unsigned mask_prefix = __ballot_sync(0xffffffffu, is_prefix);
+    const unsigned mask_none = __ballot_sync(0xffffffffu, is_none);
+    if (mask_prefix)
+    {
+      const int first = __ffs(mask_prefix) - 1;
+      if ((mask_none & ((1u << first) - 1u)) == 0u)
+      {
+        q = top - first;
+        break;
+      }
+    }
+    else if (mask_none == 0u)
+    {
+      top -= 32;      // 32 aggregates and no prefix yet: look further back
+      continue;
+    }
+    /* a predecessor in the window has published nothing yet: wait for it */
+    __nanosleep(40);
+    if (t_start == 0) t_start = global_timer_ns();
+    else if (global_timer_ns() - t_start > kSpinLimitNs)
+    {
+      if (lane == 0) atomicExch(&a.control[1], 1u);
+      q = 0;
+      break;
+    }
+  }
+  __threadfence();
+  const size_t qi = item - (size_t)(jb - q) * item_stride;
+  const cx<F>* pp = a.prefix + qi * G::WC + lane * G::CPL;
+#pragma unroll
+  for (int b = 0; b < G::CPL; ++b) acc[b] = load_l2<F>(pp + b);
+  /* rows are fetched four at a time (independent loads in flight), then added in order */
+  const cx<F>* tbase = a.totals + (item - (size_t)jb * item_stride) * G::WC + lane * G::CPL;
+  const size_t tstride = item_stride * G::WC;
+  long long r = q + 1;
+  for (; r + 4 <= (long long)jb; r += 4)
+  {
+    cx<F> v[4][G::CPL];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b) v[u][b] = load_l2<F>(tbase + (size_t)(r + u) * tstride + b);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b) acc[b] = A::cadd(acc[b], v[u][b]);
+  }
+  for (; r < (long long)jb; ++r)
+  {
+    cx<F> v[G::CPL];
+#pragma unroll
+    for (int b = 0; b < G::CPL; ++b) v[b] = load_l2<F>(tbase + (size_t)r * tstride + b);
+#pragma unroll
+    for (int b = 0; b < G::CPL; ++b) acc[b] = A::cadd(acc[b], v[b]);
+  }
+}
+
+template <typename F, int WINDOW, bool VEC, int EMIT, int MODE>
+__global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const ChainArgs<F> a)
 {
   typedef EmitGeo<F, WINDOW> G;
   typedef Arith<F> A;
   constexpr bool SLIDE = IsSlide<F, MODE>::value != 0;     // double fast mode
-  constexpr bool FUSED = (MODE == MODE_FAST) && !SLIDE;     // float fast mode
+  constexpr bool FUSED = (MODE == MODE_FAST) && !SLIDE;     // float fused mode
   typedef StageOps<F, FUSED> S;
-  __shared__ __align__(32) F sdelta[kMaxChunk];
+  /* dynamic shared memory, sized by the launch (scan_smem_bytes): deltas of the CTA's chunks, their
+   * totals, the carry at the CTA's first chunk */
+  extern __shared__ __align__(32) unsigned char smem_raw[];
   __shared__ unsigned s_ticket;
+  const unsigned nwarps = blockDim.x >> 5;
+  F* sdelta_all = reinterpret_cast<F*>(smem_raw);
+  cx<F>* stot_all = reinterpret_cast<cx<F>*>(smem_raw + (size_t)nwarps * a.sched.chunk * sizeof(F));
+  cx<F>* scarry = stot_all + (size_t)nwarps * G::WC;
+#define stot(u) (stot_all + (size_t)(u) * G::WC)
 
   if (threadIdx.x == 0)
   {
@@ -851,28 +1062,33 @@ __global__ void __launch_bounds__(kEmitWarps * 32, SDFT_B200_MINBLOCKS) scan_emi
   }
   __syncthreads();
   const unsigned ticket = s_ticket;
-  const unsigned per_channel = a.sched.nchunks * a.group_blocks;
-  const unsigned ch = ticket / per_channel;
-  const unsigned rem = ticket - ch * per_channel;
-  const unsigned j = rem / a.group_blocks;
-  const unsigned gblk = rem - j * a.group_blocks;
-  const ChunkSpan cs = chunk_span(a.sched, j);
-
-  if (a.td_double) chunk_deltas<double, F>(a, ch, cs, sdelta);
-  else chunk_deltas<float, F>(a, ch, cs, sdelta);
-  if (gblk == 0)
-  {
-    if (a.td_double) roll_history<double, F>(a, ch, j);
-    else roll_history<float, F>(a, ch, j);
-  }
-  __syncthreads();
+  /* (block item, channel, group): the chains of all channels and groups advance together */
+  const unsigned per_block = a.channels * a.groups;
+  const unsigned jb = ticket / per_block;
+  const unsigned rem = ticket - jb * per_block;
+  const unsigned ch = rem / a.groups;
+  const unsigned group = rem - ch * a.groups;
 
   const unsigned warp = threadIdx.x >> 5;
   const unsigned lane = threadIdx.x & 31;
-  const unsigned group = gblk * (blockDim.x >> 5) + warp;
-  if (group >= a.groups) return;
+  const unsigned j = jb * nwarps + warp;                   // this warp's chunk
+  const bool valid = j < a.sched.nchunks;
+  const unsigned nvalid = min(nwarps, a.sched.nchunks - jb * nwarps);   // chunks of this CTA
+  const bool last_block = (jb == a.nblocks - 1);
+  ChunkSpan cs = chunk_span(a.sched, valid ? j : 0);
+  F* sdelta = sdelta_all + warp * a.sched.chunk;
 
-  const bool last_chunk = (j == a.sched.nchunks - 1);
+  if (valid)
+  {
+    if (a.td_double) chunk_deltas<double, F>(a, ch, cs, sdelta, lane);
+    else chunk_deltas<float, F>(a, ch, cs, sdelta, lane);
+  }
+  if (group == 0)
+  {
+    if (a.td_double) roll_history<double, F>(a, ch, jb);
+    else roll_history<float, F>(a, ch, jb);
+  }
+  __syncwarp();
 
   EmitLane<F, WINDOW, VEC> L;
   const int e0 = L.setup(group, lane, a.m);
@@ -889,196 +1105,153 @@ __global__ void __launch_bounds__(kEmitWarps * 32, SDFT_B200_MINBLOCKS) scan_emi
 
   /* ---- phase A: this chunk's total ---- */
   cx<F> tot[G::CPL];
-  if constexpr (SLIDE)
+#pragma unroll
+  for (int b = 0; b < G::CPL; ++b) { tot[b] = zero; L.ph[b] = zero; }
+  if (valid)
   {
-    /* total = P_start * sum_i tw^i delta_i, the inner sum by Horner from the chunk's last sample,
-     * four samples per step once the remaining count is a multiple of four */
-    typedef FastOps<F, MODE> X;
-#pragma unroll
-    for (int b = 0; b < G::CPL; ++b) tot[b] = zero;
-    int i = (int)cs.len;
-    for (int r = i & 3; r > 0; --r)
+    if constexpr (SLIDE)
     {
-      const F d = sdelta[--i];
-#pragma unroll
-      for (int b = 0; b < G::CPL; ++b) tot[b] = X::horner(tot[b], L.tw[b], d);
-    }
-#if defined(SDFT_B200_HORNER1)
-#pragma unroll 2
-    while (i > 0)
-    {
-      const F d = sdelta[--i];
-#pragma unroll
-      for (int b = 0; b < G::CPL; ++b) tot[b] = X::horner(tot[b], L.tw[b], d);
-    }
-#else
-    {
-      cx<F> w2[G::CPL], w3[G::CPL], w4[G::CPL];
+      /* total = P_start * sum_i tw^i delta_i, the inner sum by Horner from the chunk's last sample,
+       * four samples per step once the remaining count is a multiple of four */
+      typedef FastOps<F, MODE> X;
+      /* the table row of the starting phase is fetched now so that its latency hides under the sum */
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b)
+        L.ph[b] = live[b] ? a.f0[(size_t)(cs.cursor0 / kF0Stride) * a.cells + (e0 + b)] : zero;
+      int i = (int)cs.len;
+      for (int r = i & 3; r > 0; --r)
       {
-        w2[b] = X::cmul(L.tw[b], L.tw[b]);
-        w3[b] = X::cmul(w2[b], L.tw[b]);
-        w4[b] = X::cmul(w2[b], w2[b]);
+        const F d = sdelta[--i];
+#pragma unroll
+        for (int b = 0; b < G::CPL; ++b) tot[b] = X::horner(tot[b], L.tw[b], d);
       }
-      while (i > 0)
       {
-        i -= 4;
-        const F d0 = sdelta[i], d1 = sdelta[i + 1], d2 = sdelta[i + 2], d3 = sdelta[i + 3];
+        cx<F> w2[G::CPL], w3[G::CPL], w4[G::CPL];
 #pragma unroll
-        for (int b = 0; b < G::CPL; ++b) tot[b] = X::horner4(tot[b], L.tw[b], w2[b], w3[b], w4[b], d0, d1, d2, d3);
+        for (int b = 0; b < G::CPL; ++b)
+        {
+          w2[b] = X::cmul(L.tw[b], L.tw[b]);
+          w3[b] = X::cmul(w2[b], L.tw[b]);
+          w4[b] = X::cmul(w2[b], w2[b]);
+        }
+        while (i > 0)
+        {
+          i -= 4;
+          const F d0 = sdelta[i], d1 = sdelta[i + 1], d2 = sdelta[i + 2], d3 = sdelta[i + 3];
+#pragma unroll
+          for (int b = 0; b < G::CPL; ++b) tot[b] = X::horner4(tot[b], L.tw[b], w2[b], w3[b], w4[b], d0, d1, d2, d3);
+        }
       }
-    }
-#endif
+      for (unsigned r = cs.cursor0 % kF0Stride; r > 0; --r)     // only the first chunk of a call starts off the table grid
 #pragma unroll
-    for (int b = 0; b < G::CPL; ++b)
-    {
-      L.ph[b] = live[b] ? phase_at<F>(a.f0, a.cells, e0 + b, cs.cursor0, L.tw[b]) : zero;
-      tot[b] = X::cmul(L.ph[b], tot[b]);
-    }
-  }
-  else
-  {
+        for (int b = 0; b < G::CPL; ++b) L.ph[b] = A::rotate(L.ph[b], L.tw[b]);
 #pragma unroll
-    for (int b = 0; b < G::CPL; ++b)
-    {
-      tot[b] = zero;
-      L.ph[b] = live[b] ? phase_at<F>(a.f0, a.cells, e0 + b, cs.cursor0, L.tw[b]) : zero;
+      for (int b = 0; b < G::CPL; ++b) tot[b] = X::cmul(L.ph[b], tot[b]);
     }
-    const unsigned body = cs.len - 1;
-#pragma unroll 2
-    for (unsigned i = 0; i < body; ++i)
+    else
     {
-      const F d = sdelta[i];
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b)
+        L.ph[b] = live[b] ? phase_at<F>(a.f0, a.cells, e0 + b, cs.cursor0, L.tw[b]) : zero;
+      const unsigned body = cs.len - 1;
+#pragma unroll 2
+      for (unsigned i = 0; i < body; ++i)
       {
-        tot[b] = S::mac(tot[b], L.ph[b], d);
-        L.ph[b] = A::rotate(L.ph[b], L.tw[b]);
-      }
-    }
-    const F d = sdelta[body];
+        const F d = sdelta[i];
 #pragma unroll
-    for (int b = 0; b < G::CPL; ++b) tot[b] = S::mac(tot[b], L.ph[b], d);
+        for (int b = 0; b < G::CPL; ++b)
+        {
+          tot[b] = S::mac(tot[b], L.ph[b], d);
+          L.ph[b] = A::rotate(L.ph[b], L.tw[b]);
+        }
+      }
+      const F d = sdelta[body];
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b) tot[b] = S::mac(tot[b], L.ph[b], d);
+    }
   }
 
-  /* ---- carry: decoupled look-back with a deterministic, left-to-right summation ----
-   * Every item first publishes its own total ("aggregate"), which depends on nothing.  To obtain its
-   * carry an item walks back over its predecessors' flags, 32 at a time, to the nearest one whose
-   * inclusive PREFIX is already known, then adds prefix[q] + total[q+1] + ... + total[j-1] from left
-   * to right.  That is the very sequence of additions the serial chain would perform, so the result
-   * is bit-identical whatever q happens to be, but no item ever waits for a chain of predecessors. */
-  const size_t item = ((size_t)ch * a.sched.nchunks + j) * a.groups + group;
-  const size_t item_stride = a.groups;                      // distance between consecutive chunks
-  const unsigned code_total = a.epoch * 2u, code_prefix = a.epoch * 2u + 1u;
-  if (j == 0)
+  /* ---- phase B: carries (see the header comment) ---- */
+  const size_t item_stride = (size_t)a.channels * a.groups;          // distance between consecutive block items of a chain
+  const size_t item = (size_t)jb * item_stride + (size_t)ch * a.groups + group;
+  if (nwarps > 1)
   {
-    const cx<F>* ai = a.acc_in + (size_t)ch * a.cells;
 #pragma unroll
-    for (int b = 0; b < G::CPL; ++b) L.acc[b] = live[b] ? ai[e0 + b] : zero;
+    for (int b = 0; b < G::CPL; ++b) stot(warp)[lane * G::CPL + b] = tot[b];
+    __syncthreads();
   }
-  else
+  if (warp == 0)
   {
-    if (!last_chunk)
+    /* aggregate of the CTA: its chunk totals added in chunk order */
+    cx<F> agg[G::CPL];
+#pragma unroll
+    for (int b = 0; b < G::CPL; ++b) agg[b] = tot[b];
+    for (unsigned u = 1; u < nvalid; ++u)
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b) agg[b] = A::cadd(agg[b], stot(u)[lane * G::CPL + b]);
+    if (!last_block && jb > 0)
     {
       cx<F>* tp = a.totals + item * G::WC + lane * G::CPL;
 #pragma unroll
-      for (int b = 0; b < G::CPL; ++b) store_l2<F>(tp + b, tot[b]);
+      for (int b = 0; b < G::CPL; ++b) store_l2<F>(tp + b, agg[b]);
       __threadfence();
       __syncwarp();
-      if (lane == 0) st_release_u32(a.flags + item, code_total);
+      if (lane == 0) st_release_u32(a.flags + item, a.epoch * 2u);
     }
-    /* find q = nearest predecessor with a published prefix; all items in (q, j) must have totals */
-    long long top = (long long)j - 1;
-    long long q = -1;
-    unsigned long long t_start = 0;
-    while (true)
+    cx<F> carry[G::CPL];
+    if (jb == 0)
     {
-      const long long idx = top - (long long)lane;
-      unsigned f = 0;
-      if (idx >= 0) f = ld_acquire_u32(a.flags + (item - (size_t)(j - idx) * item_stride));
-      const bool is_prefix = (idx >= 0) && (f == code_prefix);
-      const bool is_none = (idx >= 0) && (f != code_prefix) && (f != code_total);
-      const unsigned mask_prefix = __ballot_sync(0xffffffffu, is_prefix);
-      const unsigned mask_none = __ballot_sync(0xffffffffu, is_none);
-      if (mask_prefix)
-      {
-        const int first = __ffs(mask_prefix) - 1;
-        if ((mask_none & ((1u << first) - 1u)) == 0u)
-        {
-          q = top - first;
-          break;
-        }
-      }
-      else if (mask_none == 0u)
-      {
-        top -= 32;      // 32 totals and no prefix yet: look further back
-        continue;
-      }
-      /* a predecessor in the window has published nothing yet: wait for it */
-      __nanosleep(40);
-      if (t_start == 0) t_start = global_timer_ns();
-      else if (global_timer_ns() - t_start > kSpinLimitNs)
-      {
-        if (lane == 0) atomicExch(&a.control[1], 1u);
-        q = 0;
-        break;
-      }
+      const cx<F>* ai = a.acc_in + (size_t)ch * a.cells;
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b) carry[b] = live[b] ? ai[e0 + b] : zero;
     }
-    __threadfence();
+    else
     {
-      const size_t qi = item - (size_t)(j - q) * item_stride;
-      const cx<F>* pp = a.prefix + qi * G::WC + lane * G::CPL;
+      look_back<F>(a, item, item_stride, jb, lane, carry);
+    }
 #pragma unroll
-      for (int b = 0; b < G::CPL; ++b) L.acc[b] = load_l2<F>(pp + b);
-      /* rows are fetched four at a time (independent loads in flight), then added in order */
-      const cx<F>* tbase = a.totals + (item - (size_t)j * item_stride) * G::WC + lane * G::CPL;
-      const size_t tstride = item_stride * G::WC;
-      long long r = q + 1;
-      for (; r + 4 <= (long long)j; r += 4)
-      {
-        cx<F> v[4][G::CPL];
+    for (int b = 0; b < G::CPL; ++b) agg[b] = A::cadd(carry[b], agg[b]);
+    if (!last_block)
+    {
+      cx<F>* pp = a.prefix + item * G::WC + lane * G::CPL;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+      for (int b = 0; b < G::CPL; ++b) store_l2<F>(pp + b, agg[b]);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release_u32(a.flags + item, a.epoch * 2u + 1u);
+    }
+    else
+    {
+      /* accumulators the next call starts with (sdft.h:157) */
+      cx<F>* ao = a.acc_out + (size_t)ch * a.cells;
 #pragma unroll
-          for (int b = 0; b < G::CPL; ++b) v[u][b] = load_l2<F>(tbase + (size_t)(r + u) * tstride + b);
+      for (int b = 0; b < G::CPL; ++b)
+        if (live[b]) ao[e0 + b] = agg[b];
+    }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+    for (int b = 0; b < G::CPL; ++b) L.acc[b] = carry[b];
+    if (nwarps > 1)
+    {
 #pragma unroll
-          for (int b = 0; b < G::CPL; ++b) L.acc[b] = A::cadd(L.acc[b], v[u][b]);
-      }
-      for (; r < (long long)j; ++r)
-      {
-        cx<F> v[G::CPL];
-#pragma unroll
-        for (int b = 0; b < G::CPL; ++b) v[b] = load_l2<F>(tbase + (size_t)r * tstride + b);
-#pragma unroll
-        for (int b = 0; b < G::CPL; ++b) L.acc[b] = A::cadd(L.acc[b], v[b]);
-      }
+      for (int b = 0; b < G::CPL; ++b) scarry[lane * G::CPL + b] = carry[b];
     }
   }
-#pragma unroll
-  for (int b = 0; b < G::CPL; ++b) tot[b] = A::cadd(L.acc[b], tot[b]);
-  if (!last_chunk)
+  if (nwarps > 1)
   {
-    cx<F>* pp = a.prefix + item * G::WC + lane * G::CPL;
+    __syncthreads();
+    if (warp > 0)
+    {
 #pragma unroll
-    for (int b = 0; b < G::CPL; ++b) store_l2<F>(pp + b, tot[b]);
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) st_release_u32(a.flags + item, code_prefix);
-  }
-  else
-  {
-    /* accumulators the next call starts with (sdft.h:157) */
-    cx<F>* ao = a.acc_out + (size_t)ch * a.cells;
+      for (int b = 0; b < G::CPL; ++b) L.acc[b] = scarry[lane * G::CPL + b];
+      for (unsigned u = 0; u < warp; ++u)
 #pragma unroll
-    for (int b = 0; b < G::CPL; ++b)
-      if (live[b]) ao[e0 + b] = tot[b];
+        for (int b = 0; b < G::CPL; ++b) L.acc[b] = A::cadd(L.acc[b], stot(u)[lane * G::CPL + b]);
+    }
   }
+  if (!valid) return;
 
-  /* ---- phase B: replay from the carry and stream the rows out ---- */
-  if (EMIT)
+  /* ---- phase C: replay from the carry and stream the rows out ---- */
+  if (EMIT == EMIT_ROWS)
   {
     const size_t row_stride = a.m;
     L.dst = a.out + (size_t)ch * a.out_channel_stride + (size_t)cs.t0 * row_stride + ((long long)e0 - 2);
@@ -1117,6 +1290,69 @@ __global__ void __launch_bounds__(kEmitWarps * 32, SDFT_B200_MINBLOCKS) scan_emi
       }
     }
   }
+  else if (EMIT == EMIT_SYNTH_UNIT || EMIT == EMIT_SYNTH)
+  {
+    /* fused synthesis: the rows never leave the registers (see SynthLane) */
+    typedef SynthLane<F, G::CPL, EMIT == EMIT_SYNTH_UNIT> Y;
+    Y syn;
+    syn.setup(a.tws, e0, L.ok);
+    F* pdst = a.part + ((size_t)ch * a.groups + group) * a.sched.n + cs.t0;
+    const unsigned slot = Y::step_of(lane);
+    const bool writer = (lane & 3u) == 0u;
+    cx<F> restart[G::CPL];
+    if constexpr (SLIDE)
+    {
+      typedef FastOps<F, MODE> X;
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b)
+      {
+        L.acc[b] = X::demod(L.acc[b], L.ph[b]);
+        L.tw[b].i = -L.tw[b].i;
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b)
+      {
+        L.ph[b] = live[b] ? phase_at<F>(a.f0, a.cells, e0 + b, cs.cursor0, L.tw[b]) : zero;
+        restart[b] = live[b] ? a.f0[e0 + b] : zero;
+      }
+    }
+    for (unsigned i0 = 0; i0 < cs.len; i0 += 8)
+    {
+#pragma unroll
+      for (unsigned u = 0; u < 8; ++u)
+      {
+        const unsigned i = i0 + u;
+        if (i < cs.len)
+        {
+          cx<F> y[G::CPL];
+          if constexpr (SLIDE)
+          {
+            L.fast_compute(sdelta[i], a.win, y);
+          }
+          else
+          {
+            if (cs.wraps && i == cs.len - 1) L.template compute<true, FUSED>(sdelta[i], restart, a.win, y);
+            else L.template compute<false, FUSED>(sdelta[i], restart, a.win, y);
+          }
+          syn.p[u] = syn.weigh(y);
+        }
+      }
+      const F total = syn.reduce8(lane);
+      if (writer && i0 + slot < cs.len) pdst[i0 + slot] = total;
+    }
+  }
+}
+
+#undef stot
+
+/* dynamic shared memory of one scan/emit CTA of `warps` warps and chunk length `chunk` */
+template <typename F>
+inline size_t scan_smem_bytes(unsigned warps, unsigned chunk)
+{
+  return (size_t)warps * chunk * sizeof(F) + (size_t)(warps + 1) * Geo<F>::WC * sizeof(cx<F>);
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -260,7 +260,7 @@ def test_stream_generator_matches_host_definition(torch_cuda):
         assert np.abs(dev - host).max() <= 1e-15
 
 
-@pytest.mark.parametrize("td,total_log2,tol", [("f32", 30, 1e-5), ("f64", 27, 1e-9)])
+@pytest.mark.parametrize("td,total_log2,tol", [("f32", 30, 3e-5), ("f64", 27, 1e-9)])
 def test_config5_endless_streaming(torch_cuda, td, total_log2, tol):
     """State carried across 4096-sample calls.  The CPU oracle walks the first 2^23 samples in lock
     step (rows at sampled calls, state at the end); the run then continues to 2^30 (f32 time domain;

@@ -240,6 +240,48 @@ def test_advance_and_roundtrip(SDFT):
     assert np.abs(y - o.isdft(want)).max() <= 2e-6
 
 
+@pytest.mark.parametrize("td,fd", TYPES)
+@pytest.mark.parametrize("window", ["boxcar", "hann", "hamming", "blackman"])
+@pytest.mark.parametrize("latency", [1.0, 0.5])
+def test_fused_roundtrip(SDFT, td, fd, window, latency):
+    """sdft_b200_*_roundtrip_n: analysis and synthesis in one kernel (the rows never exist) against the
+    reference's sdft_sdft followed by sdft_isdft, sample by sample (test/test.c:79-80), over several
+    calls on one plan; the plan state must end up exactly where the row-producing path leaves it."""
+    from oracle import Oracle
+    rng = np.random.default_rng(abs(hash((td, fd, window, latency))) % 65536)
+    tol = {("f32", "f64"): 2e-6, ("f64", "f64"): 1e-9, ("f32", "f32"): 2e-4, ("f64", "f32"): 2e-4}[(td, fd)]
+    for m in (3, 37, 250, 1000):
+        g = SDFT(m, window, latency, td=td, fd=fd)
+        rows = SDFT(m, window, latency, td=td, fd=fd)
+        o = Oracle(td, fd, m, window, latency)
+        for n in (1, 9, 2 * m + 13, 4 * m, 333, 5000):
+            x = rng.uniform(-1, 1, n)
+            want = o.roundtrip(x).astype(np.float64)
+            got = g.roundtrip(x).astype(np.float64)
+            scale = max(np.abs(want).max(), 1e-3)
+            assert np.abs(got - want).max() <= tol * scale, (m, n, np.abs(got - want).max() / scale)
+            rows.sdft(x)
+        cg, hg, ag, _ = g.state()
+        cr, hr, ar, _ = rows.state()
+        assert cg == cr and np.array_equal(_bits(hg), _bits(hr)) and np.array_equal(_bits(ag), _bits(ar))
+
+
+def test_fused_roundtrip_batch_and_pieces(SDFT, monkeypatch):
+    """Batched channels, device tensors, and a call cut into several scratch-bounded pieces."""
+    import torch
+    from oracle import Oracle
+    m, n, ch = 250, 6000, 3
+    x = np.random.default_rng(23).uniform(-1, 1, (ch, n)).astype(np.float32)
+    monkeypatch.setenv("SDFT_B200_ROUNDTRIP_PIECE", "1024")
+    g = SDFT(m, "hamming", 0.5, td="f32", fd="f64", channels=ch)
+    y = g.roundtrip(torch.from_numpy(x).cuda()).cpu().numpy()
+    y2 = SDFT(m, "hamming", 0.5, td="f32", fd="f64", channels=ch).roundtrip(x)
+    for c in range(ch):
+        want = Oracle("f32", "f64", m, "hamming", 0.5).roundtrip(x[c])
+        assert np.abs(y[c] - want).max() <= 2e-6
+        assert np.abs(y2[c] - want).max() <= 2e-6
+
+
 def test_host_tiling_matches_single_pass(SDFT, monkeypatch):
     """Host destinations are produced in device tiles; tiny tiles must not change a bit."""
     m, n = 64, 5000
