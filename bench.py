@@ -183,6 +183,40 @@ def cpu_reference_run(samples_per_window, threads, steps, warmup):
     return agg, per_step, kind, single
 
 
+def cpu_hop_pattern(samples, threads):
+    """The reference's own usage pattern (test/test.c:79-80): sdft_sdft_n followed by sdft_isdft_n on the
+    same hop buffer, one channel per host thread, hann.  Returns analysis bin-updates/s (synthesis time included)."""
+    from oracle import cpu_reference
+    plans = [cpu_reference("f32", "f64", M, 1, 1.0, fast=True) for _ in range(threads)]
+    kind = plans[0][1]
+    rng = np.random.default_rng(SEED + 1)
+    xs = [rng.uniform(-1, 1, samples).astype(np.float32) for _ in range(threads)]
+    ys = [np.zeros(samples, np.float32) for _ in range(threads)]
+    bufs = [np.zeros((samples, M), np.complex128) for _ in range(threads)]
+    V = ctypes.c_void_p
+
+    def work(t):
+        p = plans[t][0]
+        pre = "ref_" if kind == "reference" else ""
+        a = p._fn(pre + "sdft_n", None, [V, ctypes.c_size_t, V, V])
+        b = p._fn(pre + "isdft_n", None, [V, ctypes.c_size_t, V, V])
+        a(p.h, samples, xs[t].ctypes.data_as(V), bufs[t].ctypes.data_as(V))
+        b(p.h, samples, bufs[t].ctypes.data_as(V), ys[t].ctypes.data_as(V))
+
+    def step():
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
+
+    step()
+    dt = min(step(), step())
+    return threads * samples * M / dt
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -198,7 +232,10 @@ def run_reference_arm(args, rank, world):
                                "sdft_sdft_n on host cores, bounded sample", "m": M, "sample": sample},
         "cpu_baseline": {"value": agg, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
                          "single_thread": single},
-        "e2e": {"value": agg, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": agg, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "hop_pattern": {"value": cpu_hop_pattern(2048, threads), "unit": UNIT,
+                                "sample": "sdft_sdft_n + sdft_isdft_n per hop (test/test.c:79-80), hann, 2048-sample hops, "
+                                          "%d host threads, one channel per thread" % threads}},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -450,6 +487,37 @@ def run_b200_arm(args, rank, local_rank, world):
                         "h2d_bytes_per_step": n_rt * 4, "d2h_bytes_per_step": n_rt * 4,
                         "sample": "sdft_b200_f32f64_roundtrip_n(host samples -> host samples), n=%d, m=%d, hann: "
                                   "analysis + synthesis fused in one kernel, the rows never reach memory" % (n_rt, m)}
+
+    # the same pattern through the DROP-IN calls: sdft_sdft_n(host samples -> hop buffer) and
+    # sdft_isdft_n(hop buffer -> host samples), the hop buffer being device memory the caller allocated
+    # instead of malloc; only samples cross PCIe
+    hop = 1 << 16
+    tile = torch.empty((hop, m), dtype=torch.complex128, device=dev)
+    ph = SDFT(m, "hann", 1, td="f32", fd="f64")
+    tp = ctypes.c_void_p(tile.data_ptr())
+
+    def hop_run():
+        for i in range(0, n_rt, hop):
+            ph._f("sdft_n")(ph._h, hop, ctypes.c_void_p(xr.data_ptr() + 4 * i), tp)
+            ph._f("isdft_n")(ph._h, hop, tp, ctypes.c_void_p(yr.data_ptr() + 4 * i))
+    hop_run()
+    ph._check()
+    hp_launch0 = ph.launches
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hop_run()
+    torch.cuda.synchronize()
+    t_hp = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    ph._check()
+    launches += ph.launches - hp_launch0
+    e2e["hop_pattern"] = {"value": world * args.steps * n_rt * m / t_hp, "unit": UNIT,
+                          "samples_per_s": world * args.steps * n_rt / t_hp,
+                          "h2d_bytes_per_step": n_rt * 4, "d2h_bytes_per_step": n_rt * 4,
+                          "sample": "sdft_sdft_n + sdft_isdft_n per %d-sample hop (test/test.c:79-80) on n=%d, m=%d, hann; host "
+                                    "samples in and out, the caller's hop buffer is device memory" % (hop, n_rt, m)}
+    del tile
 
     # ---- CPU baseline beside it (rank 0, N = 1) -----------------------------------------------------
     cpu = None

@@ -20,6 +20,10 @@
 #include <cstring>
 #include <new>
 #include <vector>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <atomic>
 
 using namespace sdftb200;
 
@@ -80,6 +84,9 @@ struct sdft_b200_plan
   void* phase_scratch = nullptr;   // cells complex values, introspection only
 
   Buffer samples, synth_out, tile[2], part;
+  void* stage[2] = { nullptr, nullptr };   // pinned host staging for PAGEABLE caller buffers (grow-only)
+  size_t stage_bytes[2] = { 0, 0 };
+  cudaEvent_t stage_done[2] = { nullptr, nullptr };
   Buffer prefix, chain_totals, flags;   // chained scan: inclusive prefixes, chunk totals, epoch-stamped flags
   unsigned* control = nullptr;   // [0] work ticket, [1] spin-wait timeout flag
   unsigned epoch = 0;
@@ -246,6 +253,111 @@ PtrKind classify(const void* ptr)
   return kHostPageable;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * PAGEABLE caller buffers.  The reference's callers hand over malloc'ed / NumPy memory.  A cudaMemcpy
+ * from or to pageable memory is staged by the driver on ONE thread (and blocks the calling thread), so
+ * rows would leave the GPU at a fraction of the PCIe rate.  Instead the library DMAs tiles into its own
+ * pinned staging buffers and moves them to the caller's pages with a few host threads, the copy of tile
+ * i overlapping the DMA of tile i+1.
+ * ---------------------------------------------------------------------------------------------- */
+struct CopySeg { void* dst; const void* src; size_t bytes; };
+
+class HostCopier
+{
+public:
+  static HostCopier& get()
+  {
+    static HostCopier* instance = new HostCopier();   // never destroyed: its threads outlive main()
+    return *instance;
+  }
+  /* copies all segments, cut into slices, on the pool plus the calling thread; returns when done */
+  void run(const std::vector<CopySeg>& segs)
+  {
+    const size_t slice = (size_t)4 << 20;
+    std::vector<CopySeg> work;
+    for (const CopySeg& s : segs)
+      for (size_t off = 0; off < s.bytes; off += slice)
+        work.push_back({ (char*)s.dst + off, (const char*)s.src + off, (s.bytes - off < slice) ? s.bytes - off : slice });
+    if (work.empty()) return;
+    std::lock_guard<std::mutex> one_caller(run_mutex_);   // plans on different threads take turns
+    {
+      std::unique_lock<std::mutex> lock(mutex_);
+      work_ = &work;
+      next_.store(0);
+      pending_ = work.size();
+      ++generation_;
+    }
+    wake_.notify_all();
+    drain(&work);
+    std::unique_lock<std::mutex> lock(mutex_);
+    done_.wait(lock, [&] { return pending_ == 0; });
+    work_ = nullptr;
+  }
+
+private:
+  HostCopier()
+  {
+    unsigned n = std::thread::hardware_concurrency();
+    n = (n > 2) ? n / 2 : 1;
+    if (n > 8) n = 8;
+    n = (unsigned)env_size("SDFT_B200_COPY_THREADS", n);
+    for (unsigned i = 1; i < n; ++i) std::thread([this] { loop(); }).detach();   // the caller is thread 0
+  }
+  void drain(const std::vector<CopySeg>* work)
+  {
+    size_t finished = 0;
+    while (true)
+    {
+      const size_t i = next_.fetch_add(1);
+      if (i >= work->size()) break;
+      memcpy((*work)[i].dst, (*work)[i].src, (*work)[i].bytes);
+      ++finished;
+    }
+    if (finished)
+    {
+      std::unique_lock<std::mutex> lock(mutex_);
+      pending_ -= finished;
+      if (pending_ == 0) done_.notify_all();
+    }
+  }
+  void loop()
+  {
+    unsigned long long seen = 0;
+    while (true)
+    {
+      const std::vector<CopySeg>* work = nullptr;
+      {
+        std::unique_lock<std::mutex> lock(mutex_);
+        wake_.wait(lock, [&] { return generation_ != seen; });
+        seen = generation_;
+        work = work_;
+      }
+      if (work) drain(work);
+    }
+  }
+  std::mutex mutex_, run_mutex_;
+  std::condition_variable wake_, done_;
+  const std::vector<CopySeg>* work_ = nullptr;
+  std::atomic<size_t> next_{ 0 };
+  size_t pending_ = 0;
+  unsigned long long generation_ = 0;
+};
+
+bool reserve_stage(Plan* p, int b, size_t bytes)
+{
+  if (bytes <= p->stage_bytes[b]) return true;
+  if (p->stage[b])
+  {
+    CU_TRY(p, cudaStreamSynchronize(p->copy_stream));
+    CU_TRY(p, cudaFreeHost(p->stage[b]));
+    p->stage[b] = nullptr;
+    p->stage_bytes[b] = 0;
+  }
+  CU_TRY(p, cudaMallocHost(&p->stage[b], bytes));
+  p->stage_bytes[b] = bytes;
+  return true;
+}
+
 template <typename F> size_t csize() { return sizeof(cx<F>); }
 
 /* -------- plan construction -------- */
@@ -331,6 +443,8 @@ void plan_destroy(Plan* p)
     for (cudaEvent_t e : p->prof_events[w]) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i)
   {
+    if (p->stage[i]) cudaFreeHost(p->stage[i]);
+    if (p->stage_done[i]) cudaEventDestroy(p->stage_done[i]);
     if (p->tile_ready[i]) cudaEventDestroy(p->tile_ready[i]);
     if (p->tile_free[i]) cudaEventDestroy(p->tile_free[i]);
   }
@@ -401,6 +515,7 @@ Plan* plan_create(size_t m, int window, double latency, size_t channels)
   for (int i = 0; i < 2 && e == cudaSuccess; ++i)
   {
     e = cudaEventCreateWithFlags(&p->tile_ready[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->stage_done[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->tile_free[i], cudaEventDisableTiming);
   }
   if (e != cudaSuccess)
@@ -690,6 +805,43 @@ bool do_sdft(Plan* p, size_t n, const T* samples, cx<F>* dfts)
     return true;
   };
   if (!compute(0)) return false;
+  if (classify(dfts) == kHostPageable)
+  {
+    /* device tile -> pinned staging (DMA) -> caller's pages (host threads); see HostCopier */
+    for (int b = 0; b < 2; ++b)
+      if (!reserve_stage(p, b, ch * rows * row_bytes)) return false;
+    auto dma = [&](size_t i) -> bool
+    {
+      const int b = (int)(i & 1);
+      const size_t t0 = i * rows;
+      const size_t len = (t0 + rows <= n) ? rows : n - t0;
+      CU_TRY(p, cudaStreamWaitEvent(p->copy_stream, p->tile_ready[b], 0));
+      CU_TRY(p, cudaMemcpyAsync(p->stage[b], p->tile[b].ptr, ch * len * row_bytes, cudaMemcpyDeviceToHost, p->copy_stream));
+      CU_TRY(p, cudaEventRecord(p->tile_free[b], p->copy_stream));
+      CU_TRY(p, cudaEventRecord(p->stage_done[b], p->copy_stream));
+      return true;
+    };
+    if (!dma(0)) return false;
+    std::vector<CopySeg> segs;
+    for (size_t i = 0; i < ntiles; ++i)
+    {
+      const int b = (int)(i & 1);
+      const size_t t0 = i * rows;
+      const size_t len = (t0 + rows <= n) ? rows : n - t0;
+      if (i + 1 < ntiles)
+      {
+        if (!compute(i + 1)) return false;    // its staging buffer was emptied by the host copy of tile i-1
+        if (!dma(i + 1)) return false;
+      }
+      CU_TRY(p, cudaEventSynchronize(p->stage_done[b]));
+      segs.clear();
+      for (size_t c = 0; c < ch; ++c)
+        segs.push_back({ dfts + (c * n + t0) * m, (const cx<F>*)p->stage[b] + c * len * m, len * row_bytes });
+      HostCopier::get().run(segs);
+    }
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    return true;
+  }
   for (size_t i = 0; i < ntiles; ++i)
   {
     if (i + 1 < ntiles && !compute(i + 1)) return false;
@@ -764,6 +916,44 @@ bool do_isdft(Plan* p, size_t n, const cx<F>* dfts, T* samples)
     };
     /* make sure earlier work on the compute stream that used the tiles is done */
     CU_TRY(p, cudaStreamSynchronize(p->stream));
+    if (classify(dfts) == kHostPageable)
+    {
+      /* caller's pages -> pinned staging (host threads) -> device tile (DMA); see HostCopier */
+      for (int b = 0; b < 2; ++b)
+        if (!reserve_stage(p, b, ch * rows * row_bytes)) return false;
+      std::vector<CopySeg> segs;
+      auto fill = [&](size_t i)
+      {
+        const int b = (int)(i & 1);
+        const size_t t0 = i * rows;
+        const size_t len = (t0 + rows <= n) ? rows : n - t0;
+        segs.clear();
+        for (size_t c = 0; c < ch; ++c)
+          segs.push_back({ (cx<F>*)p->stage[b] + c * len * m, dfts + (c * n + t0) * m, len * row_bytes });
+        HostCopier::get().run(segs);
+      };
+      fill(0);
+      for (size_t i = 0; i < ntiles; ++i)
+      {
+        const int b = (int)(i & 1);
+        const size_t t0 = i * rows;
+        const size_t len = (t0 + rows <= n) ? rows : n - t0;
+        if (i >= 2) CU_TRY(p, cudaStreamWaitEvent(p->copy_stream, p->tile_free[b], 0));
+        CU_TRY(p, cudaMemcpyAsync(p->tile[b].ptr, p->stage[b], ch * len * row_bytes, cudaMemcpyHostToDevice, p->copy_stream));
+        CU_TRY(p, cudaEventRecord(p->tile_ready[b], p->copy_stream));
+        CU_TRY(p, cudaEventRecord(p->stage_done[b], p->copy_stream));
+        if (i + 1 < ntiles)
+        {
+          if (i >= 1) CU_TRY(p, cudaEventSynchronize(p->stage_done[b ^ 1]));   // its previous upload has left the buffer
+          fill(i + 1);
+        }
+        CU_TRY(p, cudaStreamWaitEvent(p->stream, p->tile_ready[b], 0));
+        if (!synthesis_device<T, F>(p, len, (const cx<F>*)p->tile[b].ptr, len * m, y + t0, n)) return false;
+        CU_TRY(p, cudaEventRecord(p->tile_free[b], p->stream));
+      }
+    }
+    else
+    {
     if (!upload(0)) return false;
     for (size_t i = 0; i < ntiles; ++i)
     {
@@ -774,6 +964,7 @@ bool do_isdft(Plan* p, size_t n, const cx<F>* dfts, T* samples)
       CU_TRY(p, cudaStreamWaitEvent(p->stream, p->tile_ready[b], 0));
       if (!synthesis_device<T, F>(p, len, (const cx<F>*)p->tile[b].ptr, len * m, y + t0, n)) return false;
       CU_TRY(p, cudaEventRecord(p->tile_free[b], p->stream));
+    }
     }
   }
   if (!out_dev)

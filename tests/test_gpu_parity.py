@@ -298,6 +298,34 @@ def test_host_tiling_matches_single_pass(SDFT, monkeypatch):
     assert np.array_equal(y1, y2)
 
 
+def test_pageable_and_pinned_host_buffers_agree(SDFT, monkeypatch):
+    """Host-pointer calls: pageable caller memory goes through the library's pinned staging and host copy
+    threads, page-locked memory is the DMA target itself; both must deliver the same bytes, for rows out
+    (sdft_n) and rows in (isdft_n), across several tiles."""
+    m, n = 256, 9000
+    monkeypatch.setenv("SDFT_B200_TILE_MB", "4")
+    x = np.random.default_rng(43).uniform(-1, 1, n).astype(np.float32)
+    a = SDFT(m, "hann", 0.5, td="f32", fd="f64")
+    b = SDFT(m, "hann", 0.5, td="f32", fd="f64")
+    lib = a._lib
+    pageable = a.sdft(x)
+    nbytes = n * m * 16
+    ptr = lib.sdft_b200_host_alloc(nbytes)
+    assert ptr
+    try:
+        pinned = np.ctypeslib.as_array((ctypes.c_char * nbytes).from_address(ptr)).view(np.complex128).reshape(n, m)
+        lib.sdft_b200_f32f64_sdft_n(b._h, n, x.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(ptr))
+        b._check()
+        assert np.array_equal(_bits(pageable), _bits(pinned))
+        y_pageable = a.isdft(pageable)
+        y_pinned = np.empty(n, np.float32)
+        lib.sdft_b200_f32f64_isdft_n(b._h, n, ctypes.c_void_p(ptr), y_pinned.ctypes.data_as(ctypes.c_void_p))
+        b._check()
+        assert np.array_equal(y_pageable, y_pinned)
+    finally:
+        lib.sdft_b200_host_free(ctypes.c_void_p(ptr))
+
+
 def test_config1_testwav(SDFT, golden_dir):
     """BASELINE config 1: test/test.wav, m=1024, hann, f32 TD / f64 FD, latency 1; whole signal in
     4096-sample calls, against the oracle, the golden rows and the reference's reconstruction SNR."""
