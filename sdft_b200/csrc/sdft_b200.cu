@@ -66,6 +66,7 @@ struct sdft_b200_plan
   size_t cursor = 0;
   size_t forced_chunk = 0;
   unsigned forced_warps = 0;     // SDFT_B200_WARPS: warps per scan/emit CTA (0 = choose per plan geometry)
+  bool driver_pageable = false;  // SDFT_B200_PAGEABLE=driver: leave pageable buffers to cudaMemcpy (for comparison)
   size_t tile_bytes = 0;
   unsigned long long launches = 0;
 
@@ -484,6 +485,10 @@ Plan* plan_create(size_t m, int window, double latency, size_t channels)
   p->tile_bytes = env_size("SDFT_B200_TILE_MB", 128) << 20;
   p->forced_chunk = env_size("SDFT_B200_CHUNK", 0);
   p->forced_warps = (unsigned)env_size("SDFT_B200_WARPS", 0);
+  {
+    const char* pg = getenv("SDFT_B200_PAGEABLE");
+    p->driver_pageable = pg && !strcmp(pg, "driver");
+  }
   if (p->forced_warps > (unsigned)kScanWarps) p->forced_warps = kScanWarps;
   {
     /* double frequency domain: fast (demodulated replay) unless SDFT_B200_F64=modulated.
@@ -805,7 +810,7 @@ bool do_sdft(Plan* p, size_t n, const T* samples, cx<F>* dfts)
     return true;
   };
   if (!compute(0)) return false;
-  if (classify(dfts) == kHostPageable)
+  if (classify(dfts) == kHostPageable && !p->driver_pageable)
   {
     /* device tile -> pinned staging (DMA) -> caller's pages (host threads); see HostCopier */
     for (int b = 0; b < 2; ++b)
@@ -916,7 +921,7 @@ bool do_isdft(Plan* p, size_t n, const cx<F>* dfts, T* samples)
     };
     /* make sure earlier work on the compute stream that used the tiles is done */
     CU_TRY(p, cudaStreamSynchronize(p->stream));
-    if (classify(dfts) == kHostPageable)
+    if (classify(dfts) == kHostPageable && !p->driver_pageable)
     {
       /* caller's pages -> pinned staging (host threads) -> device tile (DMA); see HostCopier */
       for (int b = 0; b < 2; ++b)

@@ -60,6 +60,7 @@ template <typename F> struct WindowConst
   F c0, c1, c2;   // double, modulated mode: weight folded into centre / first / second neighbour taps
   F pre;          // double, fast mode: factor folded into the deltas (whole weight times one tap)
   F k0, k1;       // double, fast mode: remaining tap ratios
+  F ksum;         // double, fast mode: sum of the taps on pre-scaled data (0 for hann and blackman)
 };
 
 template <typename F>
@@ -84,6 +85,7 @@ inline WindowConst<F> make_window_const(size_t m, int window)
     case 3: k.pre = (F)(0.04) * k.w; k.k0 = (F)(0.42) / (F)(0.04); k.k1 = (F)(0.25) / (F)(0.04); break;
     default: k.pre = k.w; k.k0 = (F)1; k.k1 = (F)0; break;
   }
+  k.ksum = (window == 0) ? (F)1 : ((window == 2) ? k.k0 - (F)2 : (F)0);
   return k;
 }
 
@@ -652,16 +654,28 @@ struct EmitLane
     }
   }
 
-  /* fast mode (double): acc[] holds the DEMODULATED spectrum, tw[] holds conj(tw); ph[] is unused */
-  __device__ __forceinline__ void fast_compute(F d, const WindowConst<F>& win, cx<F>* y)
+  /* fast mode (double): tw[] holds conj(tw), ph[] is unused, and acc[] holds z_t = aux_{t-1} + delta_t,
+   * the demodulated spectrum BEFORE its rotation: aux_t = z_t conj(tw), so
+   *     z_{t+1} = z_t conj(tw) + delta_{t+1}            one Horner step, 4 FP64 instructions,
+   *     aux_t   = z_{t+1} - delta_{t+1}.
+   * The window is linear and delta is the same real number in every cell (mirror cells included), so
+   *     window(aux_t) = window(z_{t+1}) - delta_{t+1} * (sum of the taps):
+   * nothing to subtract for hann and blackman (their taps sum to zero), one real subtraction per bin
+   * for boxcar and hamming.  The caller passes d_next = delta_{t+1}, 0 after the chunk's last sample
+   * (then z_{t+1} IS aux_t), and seeds z_0 = anchor + delta_0. */
+  __device__ __forceinline__ void fast_compute(F d_next, const WindowConst<F>& win, cx<F>* y)
   {
     typedef Arith<F> A;
 #pragma unroll
-    for (int b = 0; b < G::CPL; ++b) acc[b] = A::slide(acc[b], tw[b], d);
+    for (int b = 0; b < G::CPL; ++b) acc[b] = A::horner(acc[b], tw[b], d_next);
     if (WINDOW == 0)
     {
 #pragma unroll
-      for (int b = 0; b < G::CPL; ++b) y[b] = acc[b];
+      for (int b = 0; b < G::CPL; ++b)
+      {
+        y[b].r = __dadd_rn(acc[b].r, -d_next);
+        y[b].i = acc[b].i;
+      }
     }
     else
     {
@@ -681,6 +695,12 @@ struct EmitLane
         const cx<F> p1 = (b + 1 < G::CPL) ? acc[b + 1 < G::CPL ? b + 1 : 0] : r1;
         const cx<F> p2 = (b + 2 < G::CPL) ? acc[b + 2 < G::CPL ? b + 2 : 0] : ((b + 1 < G::CPL) ? r1 : r2);
         y[b] = A::template fast_window<WINDOW>(m2, m1, acc[b], p1, p2, win);
+      }
+      if (WINDOW == 2)
+      {
+        const F corr = __dmul_rn(d_next, win.ksum);
+#pragma unroll
+        for (int b = 0; b < G::CPL; ++b) y[b].r = __dadd_rn(y[b].r, -corr);
       }
     }
   }
@@ -769,6 +789,12 @@ struct SynthLane
     for (int i = 0; i < 8; ++i) p[i] = (F)0;
     return c;
   }
+  static __device__ __forceinline__ F warp_sum(F v)
+  {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+  }
   /* which of the eight steps lane `lane` holds after reduce8 */
   static __device__ __forceinline__ unsigned step_of(unsigned lane)
   {
@@ -827,6 +853,7 @@ __global__ void synth_finish_kernel(const F* __restrict__ part, unsigned groups,
  * ---------------------------------------------------------------------------------------------- */
 constexpr int kScanWarps = 8;          // most warps (= consecutive chunks) per scan/emit CTA
 constexpr int kSmemSamples = 2048;     // deltas held per CTA: W * chunk length <= kSmemSamples
+constexpr int kDeltaPad = 4;           // per-warp padding of the delta buffer: one zero sentinel, keeps 32-byte alignment
 
 template <typename F> struct ChainArgs
 {
@@ -1050,7 +1077,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   __shared__ unsigned s_ticket;
   const unsigned nwarps = blockDim.x >> 5;
   F* sdelta_all = reinterpret_cast<F*>(smem_raw);
-  cx<F>* stot_all = reinterpret_cast<cx<F>*>(smem_raw + (size_t)nwarps * a.sched.chunk * sizeof(F));
+  cx<F>* stot_all = reinterpret_cast<cx<F>*>(smem_raw + (size_t)nwarps * (a.sched.chunk + kDeltaPad) * sizeof(F));
   cx<F>* scarry = stot_all + (size_t)nwarps * G::WC;
 #define stot(u) (stot_all + (size_t)(u) * G::WC)
 
@@ -1076,12 +1103,13 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   const unsigned nvalid = min(nwarps, a.sched.nchunks - jb * nwarps);   // chunks of this CTA
   const bool last_block = (jb == a.nblocks - 1);
   ChunkSpan cs = chunk_span(a.sched, valid ? j : 0);
-  F* sdelta = sdelta_all + warp * a.sched.chunk;
+  F* sdelta = sdelta_all + warp * (a.sched.chunk + kDeltaPad);   // [len] holds a zero sentinel, see fast_compute
 
   if (valid)
   {
     if (a.td_double) chunk_deltas<double, F>(a, ch, cs, sdelta, lane);
     else chunk_deltas<float, F>(a, ch, cs, sdelta, lane);
+    if (lane == 0) sdelta[cs.len] = (F)0;
   }
   if (group == 0)
   {
@@ -1260,14 +1288,16 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
       /* anchor the demodulated spectrum at the carry (L.ph still holds the chunk's starting phase),
        * then slide; the period's last step needs no special case: conj(tw)^(2m) = 1 */
       typedef FastOps<F, MODE> X;
+      const F d_first = sdelta[0];
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b)
       {
         L.acc[b] = X::demod(L.acc[b], L.ph[b]);
+        L.acc[b].r = __dadd_rn(L.acc[b].r, d_first);     // z_0 = aux_{-1} + delta_0, see fast_compute
         L.tw[b].i = -L.tw[b].i;
       }
 #pragma unroll 2
-      for (unsigned i = 0; i < cs.len; ++i) L.fast_step(sdelta[i], a.win, row_stride);
+      for (unsigned i = 0; i < cs.len; ++i) L.fast_step(sdelta[i + 1], a.win, row_stride);
     }
     else
     {
@@ -1303,10 +1333,12 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
     if constexpr (SLIDE)
     {
       typedef FastOps<F, MODE> X;
+      const F d_first = sdelta[0];
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b)
       {
         L.acc[b] = X::demod(L.acc[b], L.ph[b]);
+        L.acc[b].r = L.acc[b].r + d_first;               // z_0 = aux_{-1} + delta_0, see fast_compute
         L.tw[b].i = -L.tw[b].i;
       }
     }
@@ -1319,40 +1351,46 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
         restart[b] = live[b] ? a.f0[e0 + b] : zero;
       }
     }
-    for (unsigned i0 = 0; i0 < cs.len; i0 += 8)
+    /* eight steps per reduction while they last, then single steps; no branch encloses a shuffle */
+    const unsigned body = (SLIDE || !cs.wraps) ? cs.len : cs.len - 1;
+    unsigned i = 0;
+    for (; i + 8 <= body; i += 8)
     {
 #pragma unroll
       for (unsigned u = 0; u < 8; ++u)
       {
-        const unsigned i = i0 + u;
-        if (i < cs.len)
-        {
-          cx<F> y[G::CPL];
-          if constexpr (SLIDE)
-          {
-            L.fast_compute(sdelta[i], a.win, y);
-          }
-          else
-          {
-            if (cs.wraps && i == cs.len - 1) L.template compute<true, FUSED>(sdelta[i], restart, a.win, y);
-            else L.template compute<false, FUSED>(sdelta[i], restart, a.win, y);
-          }
-          syn.p[u] = syn.weigh(y);
-        }
+        cx<F> y[G::CPL];
+        if constexpr (SLIDE) L.fast_compute(sdelta[i + u + 1], a.win, y);
+        else L.template compute<false, FUSED>(sdelta[i + u], restart, a.win, y);
+        syn.p[u] = syn.weigh(y);
       }
       const F total = syn.reduce8(lane);
-      if (writer && i0 + slot < cs.len) pdst[i0 + slot] = total;
+      if (writer) pdst[i + slot] = total;
+    }
+    for (; i < body; ++i)
+    {
+      cx<F> y[G::CPL];
+      if constexpr (SLIDE) L.fast_compute(sdelta[i + 1], a.win, y);
+      else L.template compute<false, FUSED>(sdelta[i], restart, a.win, y);
+      const F total = Y::warp_sum(syn.weigh(y));
+      if (lane == 0) pdst[i] = total;
+    }
+    if (!SLIDE && cs.wraps)
+    {
+      cx<F> y[G::CPL];
+      L.template compute<true, FUSED>(sdelta[body], restart, a.win, y);
+      const F total = Y::warp_sum(syn.weigh(y));
+      if (lane == 0) pdst[body] = total;
     }
   }
 }
-
 #undef stot
 
 /* dynamic shared memory of one scan/emit CTA of `warps` warps and chunk length `chunk` */
 template <typename F>
 inline size_t scan_smem_bytes(unsigned warps, unsigned chunk)
 {
-  return (size_t)warps * chunk * sizeof(F) + (size_t)(warps + 1) * Geo<F>::WC * sizeof(cx<F>);
+  return (size_t)warps * (chunk + kDeltaPad) * sizeof(F) + (size_t)(warps + 1) * Geo<F>::WC * sizeof(cx<F>);
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -12,12 +12,8 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_r
 timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $OUT/launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > $OUT/bench_under_ncu.log 2>&1
-for fd in f64 f32; do
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_emit -s 2 -c 1 -o $OUT/prof_${fd} \
-    python tools/quick_bench.py --n 262144 --m 4096 --fd $fd --reps 1 > $OUT/ncu_full_${fd}.log 2>&1
-done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_emit -s 2 -c 1 -o $OUT/prof_fused_f64 \
-    python tools/quick_bench.py --n 262144 --m 4096 --fd f64 --reps 1 --roundtrip > $OUT/ncu_full_fused.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:synth_kernel -s 2 -c 1 -o $OUT/prof_synth_f64 \
-    python tools/quick_bench.py --n 262144 --m 4096 --fd f64 --reps 1 --synth > $OUT/ncu_full_synth.log 2>&1
+bash tools/ncu_export.sh $OUT/prof_f64 scan_emit 2 python tools/quick_bench.py --n 262144 --m 4096 --fd f64 --reps 1
+bash tools/ncu_export.sh $OUT/prof_f32 scan_emit 2 python tools/quick_bench.py --n 262144 --m 4096 --fd f32 --reps 1
+bash tools/ncu_export.sh $OUT/prof_fused_f64 scan_emit 2 python tools/quick_bench.py --n 262144 --m 4096 --fd f64 --reps 1 --roundtrip
+bash tools/ncu_export.sh $OUT/prof_synth_f64 synth_kernel 2 python tools/quick_bench.py --n 262144 --m 4096 --fd f64 --reps 1 --synth
 tail -12 $OUT/pytest_gpu.log; cat $OUT/smoke.log | tail -3; cat $OUT/bench.json; tail -3 $OUT/bench.err

@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--stream", type=int, default=0, help="samples per call; times --calls back-to-back calls")
     ap.add_argument("--calls", type=int, default=1024)
     ap.add_argument("--host", action="store_true", help="streaming with pinned host samples in / host samples out (roundtrip)")
+    ap.add_argument("--hostrows", default="", help="sdft_n + isdft_n with HOST rows: 'pageable' (numpy) or 'pinned'")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     g = SDFT(a.m, a.window, a.latency, td=a.td, fd=a.fd, channels=a.channels)
@@ -61,7 +62,30 @@ def main():
     cs = ClockSampler(0)
     cs.start()
 
-    if a.stream:
+    if a.hostrows:
+        n = a.n
+        x = (np.random.default_rng(0).uniform(-1, 1, n)).astype(np.float32 if a.td == "f32" else np.float64)
+        cdt = np.complex128 if a.fd == "f64" else np.complex64
+        if a.hostrows == "pinned":
+            rows_t = torch.empty((n, a.m), dtype=fdt).pin_memory()
+            rows = rows_t.numpy()
+        else:
+            rows = np.empty((n, a.m), cdt)
+            rows[:] = 0          # touch the pages once: first-touch faults are the caller's, not the library's
+        y = np.empty(n, x.dtype)
+        V = ctypes.c_void_p
+        fa, fs = g._f("sdft_n"), g._f("isdft_n")
+        ta, ts = [], []
+        for r in range(a.reps + 1):
+            t0 = time.perf_counter(); fa(g._h, n, x.ctypes.data_as(V), rows.ctypes.data_as(V)); t1 = time.perf_counter()
+            fs(g._h, n, rows.ctypes.data_as(V), y.ctypes.data_as(V)); t2 = time.perf_counter()
+            ta.append(t1 - t0); ts.append(t2 - t1)
+        g._check()
+        ta, ts = min(ta[1:]), min(ts[1:])
+        res.update({"mode": "hostrows-" + a.hostrows, "n": n, "pageable_path": os.environ.get("SDFT_B200_PAGEABLE", "staged"),
+                    "sdft_n_GBps": n * a.m * fdb / ta / 1e9, "isdft_n_GBps": n * a.m * fdb / ts / 1e9,
+                    "sdft_n_bin_updates_per_s": n * a.m / ta})
+    elif a.stream:
         n, calls, ch = a.stream, a.calls, a.channels
         if a.host:
             x = torch.rand(calls, ch * n, dtype=tdt).pin_memory() * 2 - 1

@@ -17,7 +17,11 @@ def main(path, needle, min_body=20):
             if m:
                 ins.append((int(m.group(1), 16), m.group(3), m.group(4)))
         print(name, len(ins), "instructions")
+        shown = 0
         for k, (addr, op, rest) in enumerate(ins):
+            if shown >= 12:
+                print("  ... (more loops not shown)")
+                break
             if op.startswith("BRA"):
                 t = re.search(r"0x([0-9a-f]+)", rest)
                 if t and int(t.group(1), 16) < addr:
@@ -25,7 +29,8 @@ def main(path, needle, min_body=20):
                     body = [o for a, o, _ in ins if tgt <= a <= addr]
                     if len(body) >= min_body:
                         c = Counter(o.split(".")[0] if not o.startswith(("STG", "LDS", "LDG", "SHFL")) else o for o in body)
-                        print("  loop 0x%x..0x%x: %d instr  %s" % (tgt, addr, len(body), dict(c.most_common(16))))
+                        print("  loop 0x%x..0x%x: %d instr  %s" % (tgt, addr, len(body), dict(c.most_common(12))))
+                        shown += 1
 
 
 if __name__ == "__main__":
