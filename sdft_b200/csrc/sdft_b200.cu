@@ -290,9 +290,11 @@ public:
     }
     wake_.notify_all();
     drain(&work);
+    /* `work` lives on this stack frame: wait until every slice is copied AND every pool thread that
+     * picked this job up has let go of it */
     std::unique_lock<std::mutex> lock(mutex_);
-    done_.wait(lock, [&] { return pending_ == 0; });
-    work_ = nullptr;
+    work_ = nullptr;                      // threads waking up late find nothing to do
+    done_.wait(lock, [&] { return pending_ == 0 && active_ == 0; });
   }
 
 private:
@@ -332,8 +334,14 @@ private:
         wake_.wait(lock, [&] { return generation_ != seen; });
         seen = generation_;
         work = work_;
+        if (work) ++active_;
       }
-      if (work) drain(work);
+      if (work)
+      {
+        drain(work);
+        std::unique_lock<std::mutex> lock(mutex_);
+        if (--active_ == 0 && pending_ == 0) done_.notify_all();
+      }
     }
   }
   std::mutex mutex_, run_mutex_;
@@ -341,6 +349,7 @@ private:
   const std::vector<CopySeg>* work_ = nullptr;
   std::atomic<size_t> next_{ 0 };
   size_t pending_ = 0;
+  size_t active_ = 0;                    // pool threads currently holding the job
   unsigned long long generation_ = 0;
 };
 

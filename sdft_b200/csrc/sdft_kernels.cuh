@@ -851,6 +851,12 @@ __global__ void synth_finish_kernel(const F* __restrict__ part, unsigned groups,
  *      that exceeds kSpinLimitNs sets *error and gives up, so a logic error shows up as a reported
  *      failure, not as a hung device.
  * ---------------------------------------------------------------------------------------------- */
+#ifndef SDFT_B200_EMIT_UNROLL
+#define SDFT_B200_EMIT_UNROLL 2        // time steps unrolled in the row loop
+#endif
+#define SDFT_B200_STR2(x) #x
+#define SDFT_B200_STR(x) SDFT_B200_STR2(x)
+#define SDFT_B200_PRAGMA_UNROLL(n) _Pragma(SDFT_B200_STR(unroll n))
 constexpr int kScanWarps = 8;          // most warps (= consecutive chunks) per scan/emit CTA
 constexpr int kSmemSamples = 2048;     // deltas held per CTA: W * chunk length <= kSmemSamples
 constexpr int kDeltaPad = 4;           // per-warp padding of the delta buffer: one zero sentinel, keeps 32-byte alignment
@@ -1296,7 +1302,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
         L.acc[b].r = __dadd_rn(L.acc[b].r, d_first);     // z_0 = aux_{-1} + delta_0, see fast_compute
         L.tw[b].i = -L.tw[b].i;
       }
-#pragma unroll 2
+SDFT_B200_PRAGMA_UNROLL(SDFT_B200_EMIT_UNROLL)
       for (unsigned i = 0; i < cs.len; ++i) L.fast_step(sdelta[i + 1], a.win, row_stride);
     }
     else
@@ -1306,7 +1312,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
       for (int b = 0; b < G::CPL; ++b)
         L.ph[b] = live[b] ? phase_at<F>(a.f0, a.cells, e0 + b, cs.cursor0, L.tw[b]) : zero;
       const unsigned body = cs.wraps ? cs.len - 1 : cs.len;
-#pragma unroll 2
+SDFT_B200_PRAGMA_UNROLL(SDFT_B200_EMIT_UNROLL)
       for (unsigned i = 0; i < body; ++i)
       {
         L.template step<false, FUSED>(sdelta[i], (const cx<F>*)nullptr, a.win, row_stride);

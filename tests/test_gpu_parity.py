@@ -326,6 +326,26 @@ def test_pageable_and_pinned_host_buffers_agree(SDFT, monkeypatch):
         lib.sdft_b200_host_free(ctypes.c_void_p(ptr))
 
 
+def test_pageable_staging_under_many_small_calls(SDFT, monkeypatch):
+    """Hammer the host copy threads: hundreds of host-pointer calls, each cut into several tiny tiles."""
+    m = 64
+    monkeypatch.setenv("SDFT_B200_TILE_MB", "1")
+    g = SDFT(m, "hann", 1, td="f32", fd="f32")
+    r = SDFT(m, "hann", 1, td="f32", fd="f32")
+    rng = np.random.default_rng(47)
+    import torch
+    for k in range(300):
+        n = int(rng.integers(1, 6000))
+        x = rng.uniform(-1, 1, n).astype(np.float32)
+        got = g.sdft(x)
+        # same kernels without host staging, cut the way the host path tiles the call (1 MiB of rows)
+        rows = (1 << 20) // (m * 8)
+        xd = torch.from_numpy(x).cuda()
+        want = torch.cat([r.sdft(xd[i:i + rows]) for i in range(0, n, rows)])
+        assert np.array_equal(_bits(got), _bits(want.cpu().numpy())), k
+        assert np.array_equal(g.isdft(got), r.isdft(want).cpu().numpy()), k
+
+
 def test_config1_testwav(SDFT, golden_dir):
     """BASELINE config 1: test/test.wav, m=1024, hann, f32 TD / f64 FD, latency 1; whole signal in
     4096-sample calls, against the oracle, the golden rows and the reference's reconstruction SNR."""
