@@ -325,6 +325,10 @@ def run_b200_arm(args, rank, local_rank, world):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the sdft_b200 path has no CPU fallback")
+    # stdout carries exactly ONE JSON line: libraries that print banners there (NCCL does) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -558,7 +562,7 @@ def run_b200_arm(args, rank, local_rank, world):
             "other_configs": extras,
             "gpu_launches": int(launches),
         }
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -99,7 +99,11 @@ typedef struct sdft_b200_plan sdft_b200_plan_t;
   /* extension: fused analysis -> synthesis round trip (the test/test.c:79-80 pattern) that never       \
    * materialises the (n, m) matrix; out[t] equals isdft(sdft(in[t])) */                                       \
   SDFT_B200_API void sdft_b200_##SFX##_roundtrip_n(sdft_b200_plan_t* plan, size_t nsamples, const TD* in,      \
-                                                   TD* out);
+                                                   TD* out);                                                   \
+  /* extension: the same with a spectral gain between analysis and synthesis: out[t] equals               \
+   * isdft(gains .* sdft(in[t])), `gains` being dftsize complex factors (host or device memory) */            \
+  SDFT_B200_API void sdft_b200_##SFX##_roundtrip_gain_n(sdft_b200_plan_t* plan, size_t nsamples, const TD* in, \
+                                                        TD* out, const FDX* gains);
 
 SDFT_B200_DECLARE(f32f32, float, sdft_b200_cf32_t)
 SDFT_B200_DECLARE(f32f64, float, sdft_b200_cf64_t)

@@ -32,6 +32,7 @@ TYPED = {
     "sdft_batch": (_V, [_P, _SZ, _P, _P]),
     "isdft_batch": (_V, [_P, _SZ, _P, _P]),
     "roundtrip_n": (_V, [_P, _SZ, _P, _P]),
+    "roundtrip_gain_n": (_V, [_P, _SZ, _P, _P, _P]),
 }
 UNTYPED = {
     "sdft_b200_last_error": (_I, [_P]),

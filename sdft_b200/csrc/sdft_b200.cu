@@ -84,7 +84,7 @@ struct sdft_b200_plan
   int acc_sel = 0;
   void* phase_scratch = nullptr;   // cells complex values, introspection only
 
-  Buffer samples, synth_out, tile[2], part;
+  Buffer samples, synth_out, tile[2], part, weights;
   void* stage[2] = { nullptr, nullptr };   // pinned host staging for PAGEABLE caller buffers (grow-only)
   size_t stage_bytes[2] = { 0, 0 };
   cudaEvent_t stage_done[2] = { nullptr, nullptr };
@@ -446,7 +446,7 @@ void plan_destroy(Plan* p)
   if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
   void* ptrs[] = { p->tw_ext, p->tws, p->f0, p->history[0], p->history[1], p->acc_state[0], p->acc_state[1], p->phase_scratch,
                    p->prefix.ptr, p->chain_totals.ptr, p->flags.ptr, p->control,
-                   p->samples.ptr, p->synth_out.ptr, p->part.ptr, p->tile[0].ptr, p->tile[1].ptr };
+                   p->samples.ptr, p->synth_out.ptr, p->part.ptr, p->weights.ptr, p->tile[0].ptr, p->tile[1].ptr };
   for (void* q : ptrs)
     if (q) cudaFree(q);
   for (int w = 0; w < 2; ++w)
@@ -647,7 +647,8 @@ unsigned scan_warps_for(const Plan* p, unsigned chunk, unsigned nchunks)
 
 /* production path: the single-pass chained scan/emit kernel (deltas and history are its prologue) */
 template <typename T, typename F>
-bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride, F* part = nullptr)
+bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride, F* part = nullptr,
+                      const cx<F>* weights = nullptr)
 {
   const unsigned m = (unsigned)p->m;
   const unsigned ch = (unsigned)p->channels;
@@ -698,14 +699,14 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   a.cells = (unsigned)p->cells;
   a.out = out;
   a.out_channel_stride = out_stride;
-  a.tws = (const cx<F>*)p->tws;
+  a.tws = weights ? weights : (const cx<F>*)p->tws;
   a.part = part;
   a.groups = groups;
   a.win = make_window_const<F>(p->m, p->window);   // sdft.h:422, :371
   if (part)
   {
     prof_mark(p, 0);
-    if (p->latency == 1) launch_chain<F, EMIT_SYNTH_UNIT>(p, a, false, warps);   // exact compare, sdft.h:639
+    if (p->latency == 1 && !weights) launch_chain<F, EMIT_SYNTH_UNIT>(p, a, false, warps);   // exact compare, sdft.h:639
     else launch_chain<F, EMIT_SYNTH>(p, a, false, warps);
     prof_mark(p, 0);
   }
@@ -1053,10 +1054,34 @@ bool do_isdft_nd(Plan* p, size_t n, const cx<F>** rows_in, T* samples)
  * its bins per time step (SynthLane), per-group partial sums go to a scratch buffer and a small second
  * kernel adds the groups in order.  Long calls are cut into pieces that bound the scratch. */
 template <typename T, typename F>
-bool do_roundtrip(Plan* p, size_t n, const T* in, T* out)
+bool do_roundtrip(Plan* p, size_t n, const T* in, T* out, const cx<F>* gains = nullptr)
 {
   if (n == 0) return true;
   CU_TRY(p, cudaSetDevice(p->device));
+  const cx<F>* weights = nullptr;
+  if (gains)
+  {
+    /* spectral processing between analysis and synthesis: every row is multiplied bin by bin with
+     * `gains` before sdft_isdft sees it, i.e. the synthesis weights become gains[k] * tws[k]
+     * (gains[k] * (-1)^k for latency 1, sdft.h:639-652) */
+    const size_t m = p->m;
+    std::vector<cx<F>> g(m), w(m);
+    if (classify(gains) == kDevice) CU_TRY(p, cudaMemcpy(g.data(), gains, m * sizeof(cx<F>), cudaMemcpyDeviceToHost));
+    else memcpy(g.data(), gains, m * sizeof(cx<F>));
+    std::vector<cx<F>> tw, tws;
+    make_tables<F>(m, p->latency, tw, tws);
+    for (size_t k = 0; k < m; ++k)
+    {
+      cx<F> t = tws[k];
+      if (p->latency == 1) { t.r = (k & 1) ? (F)(-1) : (F)(1); t.i = (F)0; }
+      w[k].r = g[k].r * t.r - g[k].i * t.i;
+      w[k].i = g[k].r * t.i + g[k].i * t.r;
+    }
+    if (!reserve(p, p->weights, m * sizeof(cx<F>))) return false;
+    CU_TRY(p, cudaMemcpyAsync(p->weights.ptr, w.data(), m * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(p, cudaStreamSynchronize(p->stream));   // w goes out of scope
+    weights = (const cx<F>*)p->weights.ptr;
+  }
   bool ok = true;
   const T* x = stage_samples<T>(p, n, in, &ok);
   if (!ok) return false;
@@ -1075,7 +1100,7 @@ bool do_roundtrip(Plan* p, size_t n, const T* in, T* out)
   for (size_t t0 = 0; t0 < n; t0 += piece)
   {
     const size_t len = (t0 + piece <= n) ? piece : n - t0;
-    if (!analysis_chained<T, F>(p, len, x + t0, n, (cx<F>*)nullptr, 0, (F*)p->part.ptr)) return false;
+    if (!analysis_chained<T, F>(p, len, x + t0, n, (cx<F>*)nullptr, 0, (F*)p->part.ptr, weights)) return false;
     size_t blocks = (len + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     synth_finish_kernel<T, F><<<dim3((unsigned)blocks, (unsigned)ch), 256, 0, p->stream>>>(
@@ -1170,6 +1195,12 @@ bool typed(Plan* p, const char* fn)
   extern "C" void sdft_b200_##SFX##_roundtrip_n(sdft_b200_plan_t* p, size_t n, const TD* in, TD* out)           \
   {                                                                                                             \
     if (typed<TD, FD>(p, "sdft_roundtrip_n: plan type mismatch")) do_roundtrip<TD, FD>(p, n, in, out);          \
+  }                                                                                                             \
+  extern "C" void sdft_b200_##SFX##_roundtrip_gain_n(sdft_b200_plan_t* p, size_t n, const TD* in, TD* out,      \
+                                                     const FDX* gains)                                          \
+  {                                                                                                             \
+    if (typed<TD, FD>(p, "sdft_roundtrip_gain_n: plan type mismatch"))                                          \
+      do_roundtrip<TD, FD>(p, n, in, out, (const cx<FD>*)gains);                                                \
   }
 
 SDFT_B200_DEFINE(f32f32, float, float, sdft_b200_cf32_t)

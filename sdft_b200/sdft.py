@@ -156,20 +156,33 @@ class SDFT:
             self._f("advance")(self._h, x.shape[-1], x.ctypes.data_as(ctypes.c_void_p))
         self._check()
 
-    def roundtrip(self, samples):
-        """isdft(sdft(samples)) without materialising the DFT matrix for the caller."""
+    def roundtrip(self, samples, gains=None):
+        """isdft(sdft(samples)) in one fused kernel: the DFT matrix never exists in memory.
+        `gains` (bins,) complex: every DFT row is multiplied with it before synthesis (a static
+        spectral filter between analysis and synthesis)."""
+        gp = None
+        if gains is not None:
+            gv = np.ascontiguousarray(gains, dtype=_NP_FD[self.fd])
+            assert gv.shape == (self.size,), f'Expected (frequencies,), got {gv.shape}!'
+            gp = gv.ctypes.data_as(ctypes.c_void_p)
+
+        def call(n, xp, yp):
+            if gp is None:
+                self._f("roundtrip_n")(self._h, n, xp, yp)
+            else:
+                self._f("roundtrip_gain_n")(self._h, n, xp, yp, gp)
+            self._check()
+
         if _is_torch_cuda(samples):
             import torch
             x = samples.to(torch.float32 if self.td == "f32" else torch.float64).contiguous()
             y = torch.empty_like(x)
             self._use_torch_stream()
-            self._f("roundtrip_n")(self._h, x.shape[-1], ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()))
-            self._check()
+            call(x.shape[-1], ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()))
             return y
         x = np.ascontiguousarray(np.atleast_1d(samples), dtype=_NP_TD[self.td])
         y = np.empty_like(x)
-        self._f("roundtrip_n")(self._h, x.shape[-1], x.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p))
-        self._check()
+        call(x.shape[-1], x.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p))
         return y
 
     def twiddles(self):

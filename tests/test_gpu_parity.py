@@ -266,6 +266,24 @@ def test_fused_roundtrip(SDFT, td, fd, window, latency):
         assert cg == cr and np.array_equal(_bits(hg), _bits(hr)) and np.array_equal(_bits(ag), _bits(ar))
 
 
+@pytest.mark.parametrize("latency", [1.0, 0.5])
+@pytest.mark.parametrize("fd", ["f32", "f64"])
+def test_fused_roundtrip_with_spectral_gain(SDFT, fd, latency):
+    """roundtrip_gain_n: isdft(gains .* sdft(x)) without the matrix; against the oracle's rows scaled on
+    the host and synthesized by the oracle."""
+    from oracle import Oracle
+    m, n = 250, 3000
+    rng = np.random.default_rng(29)
+    x = rng.uniform(-1, 1, n).astype(np.float32)
+    gains = (rng.uniform(0, 1, m) * np.exp(2j * np.pi * rng.uniform(0, 1, m))).astype(np.complex128)
+    o = Oracle("f32", fd, m, "hann", latency)
+    want = o.isdft((o.sdft(x).astype(np.complex128) * gains).astype(o.fdx_np)).astype(np.float64)
+    g = SDFT(m, "hann", latency, td="f32", fd=fd)
+    got = np.concatenate([g.roundtrip(x[:1700], gains=gains), g.roundtrip(x[1700:], gains=gains)]).astype(np.float64)
+    tol = 2e-6 if fd == "f64" else 2e-4
+    assert np.abs(got - want).max() <= tol * max(np.abs(want).max(), 1e-3)
+
+
 def test_fused_roundtrip_batch_and_pieces(SDFT, monkeypatch):
     """Batched channels, device tensors, and a call cut into several scratch-bounded pieces."""
     import torch
