@@ -140,6 +140,12 @@ SDFT_B200_API unsigned long long sdft_b200_launch_count(const sdft_b200_plan_t* 
 SDFT_B200_API int sdft_b200_set_profiling(sdft_b200_plan_t* plan, int on);
 SDFT_B200_API double sdft_b200_kernel_ms(sdft_b200_plan_t* plan, int which, unsigned long long* launches);
 
+/* Tuning aid: a library built with -DSDFT_B200_TRACE records eight %globaltimer stamps per CTA of the last
+ * analysis launch (ticket, deltas loaded, chunk total, aggregate published, carry known, replay start,
+ * rows done, unused); copies up to max_items x 8 stamps to `stamps` and returns the number of CTAs.
+ * A regular build records nothing and returns 0. */
+SDFT_B200_API size_t sdft_b200_debug_trace(sdft_b200_plan_t* plan, unsigned long long* stamps, size_t max_items);
+
 /* Introspection used by the parity tests: copies plan tables/state to HOST buffers.
  * twiddles: analysis and synthesis tables, dftsize complex values each (c/src/sdft/sdft.h:444-445).
  * state (channel): cursor, history (2*dftsize samples, oldest first), accumulators and current

@@ -50,6 +50,7 @@ UNTYPED = {
     "sdft_b200_host_alloc": (_P, [_SZ]),
     "sdft_b200_host_free": (_V, [_P]),
     "sdft_b200_version": (ctypes.c_char_p, []),
+    "sdft_b200_debug_trace": (_SZ, [_P, _P, _SZ]),
 }
 
 

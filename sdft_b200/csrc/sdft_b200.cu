@@ -85,6 +85,8 @@ struct sdft_b200_plan
   void* phase_scratch = nullptr;   // cells complex values, introspection only
 
   Buffer samples, synth_out, tile[2], part, weights;
+  Buffer trace;                  // -DSDFT_B200_TRACE builds: per-CTA phase stamps of the last scan launch
+  size_t trace_items = 0;
   void* stage[2] = { nullptr, nullptr };   // pinned host staging for PAGEABLE caller buffers (grow-only)
   size_t stage_bytes[2] = { 0, 0 };
   cudaEvent_t stage_done[2] = { nullptr, nullptr };
@@ -446,7 +448,7 @@ void plan_destroy(Plan* p)
   if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
   void* ptrs[] = { p->tw_ext, p->tws, p->f0, p->history[0], p->history[1], p->acc_state[0], p->acc_state[1], p->phase_scratch,
                    p->prefix.ptr, p->chain_totals.ptr, p->flags.ptr, p->control,
-                   p->samples.ptr, p->synth_out.ptr, p->part.ptr, p->weights.ptr, p->tile[0].ptr, p->tile[1].ptr };
+                   p->samples.ptr, p->synth_out.ptr, p->part.ptr, p->weights.ptr, p->trace.ptr, p->tile[0].ptr, p->tile[1].ptr };
   for (void* q : ptrs)
     if (q) cudaFree(q);
   for (int w = 0; w < 2; ++w)
@@ -602,7 +604,7 @@ template <typename F, int EMIT>
 void launch_chain(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps)
 {
   const dim3 grid(a.total_blocks);
-  const size_t smem = scan_smem_bytes<F>(warps, a.sched.chunk);
+  const size_t smem = scan_smem_bytes<F>(warps, a.sched.chunk) + (size_t)a.stage_rows * Geo<F>::WC * sizeof(cx<F>);
 #define SDFT_CHAIN_CASE(W, MODE)                                                                       \
   case W:                                                                                              \
     if (vec) scan_emit_kernel<F, W, true, EMIT, MODE><<<grid, warps * 32, smem, p->stream>>>(a);       \
@@ -702,7 +704,16 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   a.tws = weights ? weights : (const cx<F>*)p->tws;
   a.part = part;
   a.groups = groups;
+  a.stage_rows = scan_stage_rows<F>(warps, chunk);
   a.win = make_window_const<F>(p->m, p->window);   // sdft.h:422, :371
+  a.trace = nullptr;
+#if defined(SDFT_B200_TRACE)
+  if (reserve(p, p->trace, items * 8 * sizeof(unsigned long long)))
+  {
+    a.trace = (unsigned long long*)p->trace.ptr;
+    p->trace_items = items;
+  }
+#endif
   if (part)
   {
     prof_mark(p, 0);
@@ -1271,6 +1282,20 @@ extern "C" double sdft_b200_kernel_ms(sdft_b200_plan_t* p, int which, unsigned l
   ev.clear();
   cudaGetLastError();
   return total;
+}
+
+extern "C" size_t sdft_b200_debug_trace(sdft_b200_plan_t* p, unsigned long long* stamps, size_t max_items)
+{
+  if (!p || !p->trace.ptr || !stamps) return 0;
+  cudaSetDevice(p->device);
+  cudaStreamSynchronize(p->stream);
+  const size_t items = p->trace_items < max_items ? p->trace_items : max_items;
+  if (cudaMemcpy(stamps, p->trace.ptr, items * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return 0;
+  }
+  return items;
 }
 
 extern "C" size_t sdft_b200_channels(const sdft_b200_plan_t* p) { return p ? p->channels : 0; }

@@ -668,6 +668,28 @@ struct EmitLane
     typedef Arith<F> A;
 #pragma unroll
     for (int b = 0; b < G::CPL; ++b) acc[b] = A::horner(acc[b], tw[b], d_next);
+    fast_output(acc, d_next, win, y);
+  }
+
+  /* software-pipelined form: acc[] already holds z_{t+1}; the recurrence for step t+1 (z_{t+2}, needs
+   * d_after = delta_{t+2}) is issued FIRST so that its FP64 latency overlaps the shuffles, taps and
+   * stores of step t.  Matters when few warps share an SM (short calls): the in-order issue would
+   * otherwise expose every latency of a step before the next one starts. */
+  __device__ __forceinline__ void fast_compute_ahead(F d_next, F d_after, const WindowConst<F>& win, cx<F>* y)
+  {
+    typedef Arith<F> A;
+    cx<F> nxt[G::CPL];
+#pragma unroll
+    for (int b = 0; b < G::CPL; ++b) nxt[b] = A::horner(acc[b], tw[b], d_after);
+    fast_output(acc, d_next, win, y);
+#pragma unroll
+    for (int b = 0; b < G::CPL; ++b) acc[b] = nxt[b];
+  }
+
+  /* window(z) - d_next * (sum of taps), see fast_compute */
+  __device__ __forceinline__ void fast_output(const cx<F>* acc, F d_next, const WindowConst<F>& win, cx<F>* y)
+  {
+    typedef Arith<F> A;
     if (WINDOW == 0)
     {
 #pragma unroll
@@ -889,8 +911,25 @@ template <typename F> struct ChainArgs
   const cx<F>* tws;        // (m) synthesis twiddles, EMIT_SYNTH only
   F* part;                 // (channels, groups, n) per-group partial sums of the fused synthesis
   unsigned groups;
+  unsigned stage_rows;     // rows of look-back staging in shared memory (scan_stage_rows)
   WindowConst<F> win;
+  unsigned long long* trace;   // -DSDFT_B200_TRACE builds only: 8 %globaltimer stamps per CTA, else unused
 };
+
+#if defined(SDFT_B200_TRACE)
+#define SDFT_B200_STAMP(slot)                                                                          \
+  do                                                                                                   \
+  {                                                                                                    \
+    if (a.trace && threadIdx.x == 0)                                                                   \
+    {                                                                                                  \
+      unsigned long long t__;                                                                          \
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t__));                                           \
+      a.trace[(size_t)ticket * 8 + (slot)] = t__;                                                      \
+    }                                                                                                  \
+  } while (0)
+#else
+#define SDFT_B200_STAMP(slot) do { } while (0)
+#endif
 
 constexpr unsigned long long kSpinLimitNs = 20ull * 1000ull * 1000ull * 1000ull;
 
@@ -899,6 +938,16 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p)
+{
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu()
+{
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v)
 {
@@ -993,27 +1042,47 @@ __device__ __forceinline__ void roll_history(const ChainArgs<F>& a, unsigned ch,
 template <typename F, int MODE> struct IsSlide { enum { value = 0 }; };
 template <> struct IsSlide<double, MODE_FAST> { enum { value = 1 }; };
 
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src)
+{
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 /* carry at the first chunk of block item `jb` (jb > 0): decoupled look-back over the preceding block
- * items of the chain, deterministic left-to-right summation (one warp; see the header comment) */
+ * items of the chain, deterministic left-to-right summation (one warp; see the header comment).
+ * The walk stops at the nearest item `q` with a published inclusive prefix -- or at item 0, whose
+ * prefix is by definition acc_in + aggregate(0), so nobody waits for item 0's second publication.
+ * The rows to add (prefix or acc_in, then the aggregates q+1 .. jb-1) are fetched into the shared-memory
+ * staging area `stage` (`stage_rows` rows) with cp.async, as many at once as fit -- one memory round
+ * trip for up to stage_rows rows instead of one per four -- and then added in order. */
 template <typename F>
 __device__ __forceinline__ void look_back(const ChainArgs<F>& a, size_t item, size_t item_stride, unsigned jb, unsigned lane,
-                                          cx<F>* acc)
+                                          const cx<F>* acc_in_cells, cx<F>* stage, unsigned stage_rows, cx<F>* acc,
+                                          unsigned trace_slot)
 {
   typedef Geo<F> G;
   typedef Arith<F> A;
   const unsigned code_total = a.epoch * 2u, code_prefix = a.epoch * 2u + 1u;
   long long top = (long long)jb - 1;
   long long q = -1;
+  bool from_start = false;          // summation starts from acc_in + aggregate(0)
   unsigned long long t_start = 0;
+  unsigned spins = 0;
   while (true)
   {
     const long long idx = top - (long long)lane;
     unsigned f = 0;
-    if (idx >= 0) f = ld_acquire_u32(a.flags + (item - (size_t)(jb - idx) * item_stride));
+    if (idx >= 0) f = ld_relaxed_u32(a.flags + (item - (size_t)(jb - idx) * item_stride));   // acquire fence after the loop
     const bool is_prefix = (idx >= 0) && (f == code_prefix);
     const bool is_none = (idx >= 0) && (f != code_prefix) && (f != code_total);
     const unsigned mask_prefix = __ballot_sync(0xffffffffu, is_prefix);
     const unsigned mask_none = __ballot_sync(0xffffffffu, is_none);
+    const unsigned mask_valid = __ballot_sync(0xffffffffu, idx >= 0);
     if (mask_prefix)
     {
       const int first = __ffs(mask_prefix) - 1;
@@ -1025,47 +1094,64 @@ __device__ __forceinline__ void look_back(const ChainArgs<F>& a, size_t item, si
     }
     else if (mask_none == 0u)
     {
+      if (mask_valid != 0xffffffffu)
+      {
+        /* the window reaches item 0 and everything in it has at least its aggregate */
+        q = 0;
+        from_start = true;
+        break;
+      }
       top -= 32;      // 32 aggregates and no prefix yet: look further back
       continue;
     }
-    /* a predecessor in the window has published nothing yet: wait for it */
-    __nanosleep(40);
+    /* a predecessor in the window has published nothing yet: wait for it (spin first, it is usually
+     * a matter of a microsecond; back off and watch the clock only when it takes longer) */
+    if (++spins < 64u) continue;
+    __nanosleep(100);
     if (t_start == 0) t_start = global_timer_ns();
     else if (global_timer_ns() - t_start > kSpinLimitNs)
     {
       if (lane == 0) atomicExch(&a.control[1], 1u);
       q = 0;
+      from_start = true;
       break;
     }
   }
-  __threadfence();
-  const size_t qi = item - (size_t)(jb - q) * item_stride;
-  const cx<F>* pp = a.prefix + qi * G::WC + lane * G::CPL;
-#pragma unroll
-  for (int b = 0; b < G::CPL; ++b) acc[b] = load_l2<F>(pp + b);
-  /* rows are fetched four at a time (independent loads in flight), then added in order */
-  const cx<F>* tbase = a.totals + (item - (size_t)jb * item_stride) * G::WC + lane * G::CPL;
-  const size_t tstride = item_stride * G::WC;
-  long long r = q + 1;
-  for (; r + 4 <= (long long)jb; r += 4)
+#if defined(SDFT_B200_TRACE)
+  if (a.trace && lane == 0) a.trace[(size_t)trace_slot * 8 + 7] = global_timer_ns();   // predecessors' publications seen
+#endif
+  fence_acq_rel_gpu();      // pairs with the publishers' st.release: their rows are visible from here on
+  const cx<F>* chain0 = a.totals + (item - (size_t)jb * item_stride) * G::WC + lane * G::CPL;   // aggregate of item 0, this lane's cells
+  const cx<F>* prefix0 = a.prefix + (item - (size_t)jb * item_stride) * G::WC + lane * G::CPL;
+  const size_t rstride = item_stride * G::WC;
+  if (from_start)
   {
-    cx<F> v[4][G::CPL];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int b = 0; b < G::CPL; ++b) v[u][b] = load_l2<F>(tbase + (size_t)(r + u) * tstride + b);
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int b = 0; b < G::CPL; ++b) acc[b] = A::cadd(acc[b], v[u][b]);
+    for (int b = 0; b < G::CPL; ++b) acc[b] = acc_in_cells[b];
   }
-  for (; r < (long long)jb; ++r)
+  else
   {
-    cx<F> v[G::CPL];
 #pragma unroll
-    for (int b = 0; b < G::CPL; ++b) v[b] = load_l2<F>(tbase + (size_t)r * tstride + b);
+    for (int b = 0; b < G::CPL; ++b) acc[b] = load_l2<F>(prefix0 + (size_t)q * rstride + b);
+  }
+  long long r = from_start ? 0 : q + 1;
+  cx<F>* mine = stage + lane * G::CPL;
+  constexpr int kVec = (int)(G::CPL * sizeof(cx<F>) / 16);      // 16-byte pieces of this lane's cells in one row
+  while (r < (long long)jb)
+  {
+    const unsigned batch = (unsigned)min((long long)stage_rows, (long long)jb - r);
+    for (unsigned u = 0; u < batch; ++u)
+    {
+      const char* src = reinterpret_cast<const char*>(chain0 + (size_t)(r + u) * rstride);
+      char* dst = reinterpret_cast<char*>(mine + (size_t)u * G::WC);
 #pragma unroll
-    for (int b = 0; b < G::CPL; ++b) acc[b] = A::cadd(acc[b], v[b]);
+      for (int v = 0; v < kVec; ++v) cp_async_16(dst + 16 * v, src + 16 * v);
+    }
+    cp_async_wait_all();
+    for (unsigned u = 0; u < batch; ++u)
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b) acc[b] = A::cadd(acc[b], mine[(size_t)u * G::WC + b]);
+    r += batch;
   }
 }
 
@@ -1085,6 +1171,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   F* sdelta_all = reinterpret_cast<F*>(smem_raw);
   cx<F>* stot_all = reinterpret_cast<cx<F>*>(smem_raw + (size_t)nwarps * (a.sched.chunk + kDeltaPad) * sizeof(F));
   cx<F>* scarry = stot_all + (size_t)nwarps * G::WC;
+  cx<F>* sstage = scarry + G::WC;                            // look-back staging, a.stage_rows rows
 #define stot(u) (stot_all + (size_t)(u) * G::WC)
 
   if (threadIdx.x == 0)
@@ -1095,6 +1182,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   }
   __syncthreads();
   const unsigned ticket = s_ticket;
+  SDFT_B200_STAMP(0);   // ticket taken
   /* (block item, channel, group): the chains of all channels and groups advance together */
   const unsigned per_block = a.channels * a.groups;
   const unsigned jb = ticket / per_block;
@@ -1115,7 +1203,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   {
     if (a.td_double) chunk_deltas<double, F>(a, ch, cs, sdelta, lane);
     else chunk_deltas<float, F>(a, ch, cs, sdelta, lane);
-    if (lane == 0) sdelta[cs.len] = (F)0;
+    if (lane < 2) sdelta[cs.len + lane] = (F)0;
   }
   if (group == 0)
   {
@@ -1123,6 +1211,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
     else roll_history<float, F>(a, ch, jb);
   }
   __syncwarp();
+  SDFT_B200_STAMP(1);   // deltas in shared memory
 
   EmitLane<F, WINDOW, VEC> L;
   const int e0 = L.setup(group, lane, a.m);
@@ -1205,6 +1294,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
     }
   }
 
+  SDFT_B200_STAMP(2);   // chunk total done
   /* ---- phase B: carries (see the header comment) ---- */
   const size_t item_stride = (size_t)a.channels * a.groups;          // distance between consecutive block items of a chain
   const size_t item = (size_t)jb * item_stride + (size_t)ch * a.groups + group;
@@ -1223,26 +1313,31 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
     for (unsigned u = 1; u < nvalid; ++u)
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b) agg[b] = A::cadd(agg[b], stot(u)[lane * G::CPL + b]);
-    if (!last_block && jb > 0)
+    if (!last_block)
     {
       cx<F>* tp = a.totals + item * G::WC + lane * G::CPL;
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b) store_l2<F>(tp + b, agg[b]);
-      __threadfence();
+      /* the warp barrier orders every lane's stores before lane 0's release store, and a release is
+       * cumulative: whoever acquires the flag sees the whole row (one fence instead of 32) */
       __syncwarp();
       if (lane == 0) st_release_u32(a.flags + item, a.epoch * 2u);
     }
+    SDFT_B200_STAMP(3);   // aggregate published
     cx<F> carry[G::CPL];
-    if (jb == 0)
     {
       const cx<F>* ai = a.acc_in + (size_t)ch * a.cells;
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b) carry[b] = live[b] ? ai[e0 + b] : zero;
     }
-    else
+    if (jb > 0)
     {
-      look_back<F>(a, item, item_stride, jb, lane, carry);
+      cx<F> start[G::CPL];
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b) start[b] = carry[b];
+      look_back<F>(a, item, item_stride, jb, lane, start, sstage, a.stage_rows, carry, ticket);
     }
+    SDFT_B200_STAMP(4);   // carry known
 #pragma unroll
     for (int b = 0; b < G::CPL; ++b) agg[b] = A::cadd(carry[b], agg[b]);
     if (!last_block)
@@ -1250,7 +1345,6 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
       cx<F>* pp = a.prefix + item * G::WC + lane * G::CPL;
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b) store_l2<F>(pp + b, agg[b]);
-      __threadfence();
       __syncwarp();
       if (lane == 0) st_release_u32(a.flags + item, a.epoch * 2u + 1u);
     }
@@ -1282,6 +1376,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
         for (int b = 0; b < G::CPL; ++b) L.acc[b] = A::cadd(L.acc[b], stot(u)[lane * G::CPL + b]);
     }
   }
+  SDFT_B200_STAMP(5);   // carries distributed, replay starts
   if (!valid) return;
 
   /* ---- phase C: replay from the carry and stream the rows out ---- */
@@ -1302,8 +1397,23 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
         L.acc[b].r = __dadd_rn(L.acc[b].r, d_first);     // z_0 = aux_{-1} + delta_0, see fast_compute
         L.tw[b].i = -L.tw[b].i;
       }
+#if defined(SDFT_B200_NO_PIPELINE)
 SDFT_B200_PRAGMA_UNROLL(SDFT_B200_EMIT_UNROLL)
       for (unsigned i = 0; i < cs.len; ++i) L.fast_step(sdelta[i + 1], a.win, row_stride);
+#else
+      {
+        const F d1 = sdelta[1];
+#pragma unroll
+        for (int b = 0; b < G::CPL; ++b) L.acc[b] = A::horner(L.acc[b], L.tw[b], d1);      // z_1
+      }
+SDFT_B200_PRAGMA_UNROLL(SDFT_B200_EMIT_UNROLL)
+      for (unsigned i = 0; i < cs.len; ++i)
+      {
+        cx<F> y[G::CPL];
+        L.fast_compute_ahead(sdelta[i + 1], sdelta[i + 2], a.win, y);   // [len], [len + 1] are zero sentinels
+        L.store_rows(y, row_stride);
+      }
+#endif
     }
     else
     {
@@ -1389,6 +1499,7 @@ SDFT_B200_PRAGMA_UNROLL(SDFT_B200_EMIT_UNROLL)
       if (lane == 0) pdst[body] = total;
     }
   }
+  SDFT_B200_STAMP(6);   // warp 0 finished its rows
 }
 #undef stot
 
@@ -1397,6 +1508,17 @@ template <typename F>
 inline size_t scan_smem_bytes(unsigned warps, unsigned chunk)
 {
   return (size_t)warps * (chunk + kDeltaPad) * sizeof(F) + (size_t)(warps + 1) * Geo<F>::WC * sizeof(cx<F>);
+}
+/* rows of look-back staging that fit next to it under the 48 KiB a CTA gets without opting in */
+template <typename F>
+inline unsigned scan_stage_rows(unsigned warps, unsigned chunk)
+{
+  const size_t row = Geo<F>::WC * sizeof(cx<F>);
+  const size_t base = scan_smem_bytes<F>(warps, chunk);
+  size_t rows = ((size_t)48 * 1024 - base) / row;
+  if (rows > 16) rows = 16;
+  if (rows < 2) rows = 2;
+  return (unsigned)rows;
 }
 
 /* ------------------------------------------------------------------------------------------------

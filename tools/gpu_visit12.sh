@@ -1,0 +1,26 @@
+#!/bin/bash
+OUT=gpurun_out/v12; mkdir -p $OUT
+timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log
+tail -4 $OUT/pytest_gpu.log
+export SDFT_B200_LIB=$PWD/sdft_b200/libsdft_b200_trace.so
+for args in "--n 4096 --m 512" "--n 16384 --m 4096"; do
+  echo "== $args"; timeout 200 python tools/trace_call.py $args 2>&1 | tail -11
+done > $OUT/trace.txt 2>&1
+cat $OUT/trace.txt
+unset SDFT_B200_LIB
+R=$OUT/sweep.jsonl; : > $R
+qb() { timeout 300 python tools/quick_bench.py "$@" >> $R 2>> $OUT/sweep.err; }
+qb --n 1048576 --m 4096 --fd f64 --window hann --reps 12
+qb --n 1048576 --m 4096 --fd f32 --window hann --reps 12
+qb --stream 4096 --calls 2048 --m 512 --fd f64 --reps 3
+qb --stream 1024 --calls 2048 --m 1024 --fd f64 --reps 3
+qb --stream 4096 --calls 2048 --m 512 --fd f64 --reps 3 --channels 16
+qb --n 16384 --m 4096 --fd f64 --window hann --reps 20
+qb --n 65536 --m 1024 --fd f64 --window hann --reps 20
+qb --n 65536 --m 2048 --fd f32 --window hann --latency 0.5 --reps 20
+python - <<'PY'
+import json
+for l in open("gpurun_out/v12/sweep.jsonl"):
+    d=json.loads(l)
+    print(d["mode"], d["m"], d["fd"], d["channels"], d.get("n", d.get("n_per_call")), ("GB/s %.0f" % d["GBps"]) if "GBps" in d else "", ("us/call %.1f" % d["us_per_call"]) if "us_per_call" in d else "ms %.3f" % d["ms"])
+PY
