@@ -67,6 +67,7 @@ struct sdft_b200_plan
   size_t forced_chunk = 0;
   unsigned forced_warps = 0;     // SDFT_B200_WARPS: warps per scan/emit CTA (0 = choose per plan geometry)
   bool driver_pageable = false;  // SDFT_B200_PAGEABLE=driver: leave pageable buffers to cudaMemcpy (for comparison)
+  bool pdl = true;               // SDFT_B200_PDL=0: plain stream-ordered launches
   size_t tile_bytes = 0;
   unsigned long long launches = 0;
 
@@ -499,6 +500,7 @@ Plan* plan_create(size_t m, int window, double latency, size_t channels)
   {
     const char* pg = getenv("SDFT_B200_PAGEABLE");
     p->driver_pageable = pg && !strcmp(pg, "driver");
+    p->pdl = env_size("SDFT_B200_PDL", 1) != 0;
   }
   if (p->forced_warps > (unsigned)kScanWarps) p->forced_warps = kScanWarps;
   {
@@ -605,10 +607,24 @@ void launch_chain(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps)
 {
   const dim3 grid(a.total_blocks);
   const size_t smem = scan_smem_bytes<F>(warps, a.sched.chunk) + (size_t)a.stage_rows * Geo<F>::WC * sizeof(cx<F>);
+  /* programmatic dependent launch: the CTAs of this call may become resident while the previous kernel
+   * of the stream drains; they wait at the top of the kernel (griddepcontrol.wait) until that kernel
+   * has completed and flushed, so nothing else about the ordering changes.  Hides the launch latency
+   * between back-to-back calls (streaming). */
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = p->pdl ? 1 : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(warps * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = p->stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
 #define SDFT_CHAIN_CASE(W, MODE)                                                                       \
   case W:                                                                                              \
-    if (vec) scan_emit_kernel<F, W, true, EMIT, MODE><<<grid, warps * 32, smem, p->stream>>>(a);       \
-    else scan_emit_kernel<F, W, false, EMIT, MODE><<<grid, warps * 32, smem, p->stream>>>(a);          \
+    if (vec) cudaLaunchKernelEx(&cfg, scan_emit_kernel<F, W, true, EMIT, MODE>, a);                    \
+    else cudaLaunchKernelEx(&cfg, scan_emit_kernel<F, W, false, EMIT, MODE>, a);                       \
     break;
   if (p->mode == MODE_FAST)
   {

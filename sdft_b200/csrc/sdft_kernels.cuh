@@ -1174,6 +1174,11 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   cx<F>* sstage = scarry + G::WC;                            // look-back staging, a.stage_rows rows
 #define stot(u) (stot_all + (size_t)(u) * G::WC)
 
+  /* programmatic dependent launch (see launch_chain): nothing of the previous kernel in the stream may be
+   * read or overwritten before it has completed; dependents of THIS kernel may start filling SMs as
+   * soon as every CTA of it has got this far */
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
   if (threadIdx.x == 0)
   {
     const unsigned t = atomicAdd(&a.control[0], 1u);

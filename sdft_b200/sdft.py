@@ -40,6 +40,15 @@ def _is_torch_cuda(x):
     return type(x).__module__.startswith("torch") and hasattr(x, "is_cuda") and x.is_cuda
 
 
+def _device_view(x):
+    """CUDA tensors pass through; any other object exposing __cuda_array_interface__ (CuPy, Numba, ...) is
+    wrapped zero-copy as a torch tensor; host data is returned unchanged."""
+    if _is_torch_cuda(x) or not hasattr(x, "__cuda_array_interface__"):
+        return x
+    import torch
+    return torch.as_tensor(x, device="cuda")
+
+
 class SDFT:
     """Sliding Discrete Fourier Transform (SDFT) on a B200."""
 
@@ -95,6 +104,7 @@ class SDFT:
 
         Returns (samples, bins); for a batch plan the input is (channels, samples) and the result
         (channels, samples, bins).  `out` (CUDA tensors only) reuses a caller-owned result tensor."""
+        samples = _device_view(samples)
         if _is_torch_cuda(samples):
             import torch
             x = samples.to(torch.float32 if self.td == "f32" else torch.float64).contiguous()
@@ -124,6 +134,7 @@ class SDFT:
 
     def isdft(self, dfts):
         """Synthesize the sample array from the given DFT matrix (sdft.py:122-145)."""
+        dfts = _device_view(dfts)
         if _is_torch_cuda(dfts):
             import torch
             d = dfts.to(torch.complex64 if self.fd == "f32" else torch.complex128).contiguous()
@@ -146,6 +157,7 @@ class SDFT:
     # ---- extensions ------------------------------------------------------------------------------
     def advance(self, samples):
         """Update the analysis state with ``samples`` without producing rows (time-shard priming)."""
+        samples = _device_view(samples)
         if _is_torch_cuda(samples):
             import torch
             x = samples.to(torch.float32 if self.td == "f32" else torch.float64).contiguous()
@@ -173,6 +185,7 @@ class SDFT:
                 self._f("roundtrip_gain_n")(self._h, n, xp, yp, gp)
             self._check()
 
+        samples = _device_view(samples)
         if _is_torch_cuda(samples):
             import torch
             x = samples.to(torch.float32 if self.td == "f32" else torch.float64).contiguous()

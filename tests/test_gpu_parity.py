@@ -224,6 +224,24 @@ def test_device_pointers_and_batch(SDFT):
     assert rel_err(got2, got) <= 1e-13   # one 3000-sample call vs three calls: other chunking, same rows
 
 
+def test_cuda_array_interface_inputs(SDFT):
+    """Anything that exposes __cuda_array_interface__ is taken zero-copy (CuPy, Numba, ...)."""
+    import torch
+
+    class Foreign:
+        def __init__(self, t):
+            self._t = t
+            self.__cuda_array_interface__ = t.__cuda_array_interface__
+
+    x = np.random.default_rng(3).uniform(-1, 1, 500).astype(np.float32)
+    a, b = SDFT(32, "hann", 1, td="f32", fd="f64"), SDFT(32, "hann", 1, td="f32", fd="f64")
+    xt = torch.from_numpy(x).cuda()
+    got = a.sdft(Foreign(xt))
+    want = b.sdft(xt)
+    assert torch.equal(got, want)
+    assert torch.equal(a.isdft(Foreign(got)), b.isdft(want))
+
+
 def test_advance_and_roundtrip(SDFT):
     from oracle import Oracle
     m = 128
