@@ -21,6 +21,7 @@ DEPENDS = SOURCES + [os.path.join(CSRC, "sdft_kernels.cuh"),
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
+    "-split-compile", "0",          # ptxas over the ~120 kernel variants in parallel (same code, a third of the time)
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",
     "-shared",
 ]

@@ -66,6 +66,7 @@ struct sdft_b200_plan
   size_t cursor = 0;
   size_t forced_chunk = 0;
   unsigned forced_warps = 0;     // SDFT_B200_WARPS: warps per scan/emit CTA (0 = choose per plan geometry)
+  int forced_geo = -1;           // SDFT_B200_GEO=wide|narrow: warp geometry (default: per call, choose_geo)
   bool driver_pageable = false;  // SDFT_B200_PAGEABLE=driver: leave pageable buffers to cudaMemcpy (for comparison)
   bool pdl = true;               // SDFT_B200_PDL=0: plain stream-ordered launches
   size_t tile_bytes = 0;
@@ -501,6 +502,9 @@ Plan* plan_create(size_t m, int window, double latency, size_t channels)
     const char* pg = getenv("SDFT_B200_PAGEABLE");
     p->driver_pageable = pg && !strcmp(pg, "driver");
     p->pdl = env_size("SDFT_B200_PDL", 1) != 0;
+    const char* ge = getenv("SDFT_B200_GEO");
+    if (ge && !strcmp(ge, "wide")) p->forced_geo = GEO_WIDE;
+    if (ge && !strcmp(ge, "narrow")) p->forced_geo = GEO_NARROW;
   }
   if (p->forced_warps > (unsigned)kScanWarps) p->forced_warps = kScanWarps;
   {
@@ -566,23 +570,46 @@ void prof_mark(Plan* p, int which)
   p->prof_events[which].push_back(e);
 }
 
-unsigned groups_for(const Plan* p)
+/* warp-wide groups of bins the plan's m bins are cut into, for either warp geometry */
+unsigned groups_for(const Plan* p, int geo = GEO_WIDE)
 {
-  const unsigned wc = (p->fd == kF32) ? (unsigned)Geo<float>::WC : (unsigned)Geo<double>::WC;
-  const unsigned halo = (p->window == 0) ? 0u : ((p->fd == kF32) ? (unsigned)Geo<float>::GROUP : (unsigned)Geo<double>::GROUP);
+  unsigned wc, halo;
+  if (p->fd == kF32)
+  {
+    wc = geo == GEO_WIDE ? (unsigned)Geo<float, GEO_WIDE>::WC : (unsigned)Geo<float, GEO_NARROW>::WC;
+    halo = (unsigned)Geo<float, GEO_WIDE>::GROUP;
+  }
+  else
+  {
+    wc = geo == GEO_WIDE ? (unsigned)Geo<double, GEO_WIDE>::WC : (unsigned)Geo<double, GEO_NARROW>::WC;
+    halo = (unsigned)Geo<double, GEO_WIDE>::GROUP;
+  }
+  if (p->window == 0) halo = 0;
   const unsigned span = wc - 2 * halo;
   return (unsigned)((p->m + span - 1) / span);
+}
+
+/* narrow warps for short calls (see Geo<F, GEO_NARROW>); only the default arithmetic modes carry
+ * narrow kernels */
+constexpr double kNarrowBelow = 1.5e6;   // total wide warp-steps of a call below which narrow warps win (profiles/r01_geo_sweep.md)
+int choose_geo(const Plan* p, size_t n)
+{
+  const bool default_mode = (p->fd == kF64) ? (p->mode == MODE_FAST) : (p->mode == MODE_MODULATED);
+  if (!default_mode) return GEO_WIDE;
+  if (p->forced_geo >= 0) return p->forced_geo;
+  const double u = (double)n * (double)groups_for(p, GEO_WIDE) * (double)p->channels;
+  return u < kNarrowBelow ? GEO_NARROW : GEO_WIDE;
 }
 
 /* 32-byte group stores need rows that start on a 32-byte boundary */
 template <typename F>
 bool can_vectorize(size_t m, const void* out, size_t out_stride)
 {
-  const size_t g = Geo<F>::GROUP;
+  const size_t g = Geo<F, GEO_WIDE>::GROUP;
   return (m % g == 0) && (((uintptr_t)out) % 32 == 0) && (out_stride % g == 0);
 }
 
-unsigned choose_chunk(const Plan* p, size_t n)
+unsigned choose_chunk(const Plan* p, size_t n, int geo)
 {
   if (p->forced_chunk)
   {
@@ -594,7 +621,15 @@ unsigned choose_chunk(const Plan* p, size_t n)
   /* Measured on B200 (tools/chunk_sweep.py, profiles/r01_chunk_sweep.md): the best chunk length is a
    * function of the call's total warp-steps U = samples x groups x channels.  Short chunks expose the
    * per-chunk latencies (ticket, table loads, look-back), long chunks leave SMs without work. */
-  const double u = (double)n * (double)groups_for(p) * (double)p->channels;
+  const double u = (double)n * (double)groups_for(p, GEO_WIDE) * (double)p->channels;
+  if (geo == GEO_NARROW)
+  {
+    /* profiles/r01_geo_sweep.md: narrow warps like longer chunks earlier, but never so long that a chain
+     * has fewer than 16 chunks */
+    unsigned c = (u < 16384.0) ? 32u : ((u < 30.0e3) ? 64u : 128u);
+    while (c > 32u && (size_t)c * 16 > n) c >>= 1;
+    return c;
+  }
   if (u < 16384.0) return 32;
   if (u < 100.0e3) return 64;
   if (u < 4.0e6) return 128;
@@ -602,11 +637,12 @@ unsigned choose_chunk(const Plan* p, size_t n)
   return kAutoChunk;
 }
 
-template <typename F, int EMIT>
-void launch_chain(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps)
+template <typename F, int EMIT, int GEO>
+void launch_chain_geo(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps)
 {
   const dim3 grid(a.total_blocks);
-  const size_t smem = scan_smem_bytes<F>(warps, a.sched.chunk) + (size_t)a.stage_rows * Geo<F>::WC * sizeof(cx<F>);
+  const size_t smem = scan_smem_bytes<F, GEO>(warps, a.sched.chunk) + (size_t)a.stage_rows * Geo<F, GEO>::WC * sizeof(cx<F>);
+  constexpr int kDefaultMode = (sizeof(F) == sizeof(double)) ? (int)MODE_FAST : (int)MODE_MODULATED;
   /* programmatic dependent launch: the CTAs of this call may become resident while the previous kernel
    * of the stream drains; they wait at the top of the kernel (griddepcontrol.wait) until that kernel
    * has completed and flushed, so nothing else about the ordering changes.  Hides the launch latency
@@ -623,31 +659,40 @@ void launch_chain(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps)
   cfg.numAttrs = 1;
 #define SDFT_CHAIN_CASE(W, MODE)                                                                       \
   case W:                                                                                              \
-    if (vec) cudaLaunchKernelEx(&cfg, scan_emit_kernel<F, W, true, EMIT, MODE>, a);                    \
-    else cudaLaunchKernelEx(&cfg, scan_emit_kernel<F, W, false, EMIT, MODE>, a);                       \
+    if (vec) cudaLaunchKernelEx(&cfg, scan_emit_kernel<F, W, true, EMIT, MODE, GEO>, a);               \
+    else cudaLaunchKernelEx(&cfg, scan_emit_kernel<F, W, false, EMIT, MODE, GEO>, a);                  \
     break;
-  if (p->mode == MODE_FAST)
+  if (GEO == GEO_NARROW || p->mode == kDefaultMode)
   {
+    /* the narrow geometry exists for the default mode only (choose_geo) */
     switch (p->window)
     {
-      SDFT_CHAIN_CASE(0, MODE_FAST)
-      SDFT_CHAIN_CASE(1, MODE_FAST)
-      SDFT_CHAIN_CASE(2, MODE_FAST)
-      SDFT_CHAIN_CASE(3, MODE_FAST)
+      SDFT_CHAIN_CASE(0, kDefaultMode)
+      SDFT_CHAIN_CASE(1, kDefaultMode)
+      SDFT_CHAIN_CASE(2, kDefaultMode)
+      SDFT_CHAIN_CASE(3, kDefaultMode)
     }
   }
-  else
+  else if constexpr (GEO == GEO_WIDE)
   {
+    constexpr int kOtherMode = (kDefaultMode == (int)MODE_FAST) ? (int)MODE_MODULATED : (int)MODE_FAST;
     switch (p->window)
     {
-      SDFT_CHAIN_CASE(0, MODE_MODULATED)
-      SDFT_CHAIN_CASE(1, MODE_MODULATED)
-      SDFT_CHAIN_CASE(2, MODE_MODULATED)
-      SDFT_CHAIN_CASE(3, MODE_MODULATED)
+      SDFT_CHAIN_CASE(0, kOtherMode)
+      SDFT_CHAIN_CASE(1, kOtherMode)
+      SDFT_CHAIN_CASE(2, kOtherMode)
+      SDFT_CHAIN_CASE(3, kOtherMode)
     }
   }
 #undef SDFT_CHAIN_CASE
   p->launches++;
+}
+
+template <typename F, int EMIT>
+void launch_chain(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps, int geo)
+{
+  if (geo == GEO_NARROW) launch_chain_geo<F, EMIT, GEO_NARROW>(p, a, vec, warps);
+  else launch_chain_geo<F, EMIT, GEO_WIDE>(p, a, vec, warps);
 }
 
 /* warps (= consecutive chunks) per scan/emit CTA */
@@ -670,9 +715,11 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
 {
   const unsigned m = (unsigned)p->m;
   const unsigned ch = (unsigned)p->channels;
-  const unsigned chunk = choose_chunk(p, n);
+  const int geo = choose_geo(p, n);
+  const unsigned chunk = choose_chunk(p, n, geo);
   const Schedule sched = make_schedule(p->cursor, n, m, chunk);
-  const unsigned groups = groups_for(p);
+  const unsigned groups = groups_for(p, geo);
+  const size_t wc = (geo == GEO_NARROW) ? (size_t)Geo<F, GEO_NARROW>::WC : (size_t)Geo<F, GEO_WIDE>::WC;
   const unsigned warps = scan_warps_for(p, chunk, sched.nchunks);
   const unsigned nblocks = (sched.nchunks + warps - 1) / warps;
   const size_t items = (size_t)ch * nblocks * groups;
@@ -682,8 +729,8 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
     return false;
   }
 
-  if (!reserve(p, p->prefix, items * Geo<F>::WC * sizeof(cx<F>))) return false;
-  if (!reserve(p, p->chain_totals, items * Geo<F>::WC * sizeof(cx<F>))) return false;
+  if (!reserve(p, p->prefix, items * wc * sizeof(cx<F>))) return false;
+  if (!reserve(p, p->chain_totals, items * wc * sizeof(cx<F>))) return false;
   const size_t flags_before = p->flags.bytes;
   if (!reserve(p, p->flags, items * sizeof(unsigned))) return false;
   if (p->flags.bytes != flags_before || p->epoch >= 0x7ffffff0u)
@@ -720,7 +767,7 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   a.tws = weights ? weights : (const cx<F>*)p->tws;
   a.part = part;
   a.groups = groups;
-  a.stage_rows = scan_stage_rows<F>(warps, chunk);
+  a.stage_rows = (geo == GEO_NARROW) ? scan_stage_rows<F, GEO_NARROW>(warps, chunk) : scan_stage_rows<F, GEO_WIDE>(warps, chunk);
   a.win = make_window_const<F>(p->m, p->window);   // sdft.h:422, :371
   a.trace = nullptr;
 #if defined(SDFT_B200_TRACE)
@@ -733,20 +780,20 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   if (part)
   {
     prof_mark(p, 0);
-    if (p->latency == 1 && !weights) launch_chain<F, EMIT_SYNTH_UNIT>(p, a, false, warps);   // exact compare, sdft.h:639
-    else launch_chain<F, EMIT_SYNTH>(p, a, false, warps);
+    if (p->latency == 1 && !weights) launch_chain<F, EMIT_SYNTH_UNIT>(p, a, false, warps, geo);   // exact compare, sdft.h:639
+    else launch_chain<F, EMIT_SYNTH>(p, a, false, warps, geo);
     prof_mark(p, 0);
   }
   else if (out)
   {
     const bool vec = can_vectorize<F>(m, out, out_stride);
     prof_mark(p, 0);
-    launch_chain<F, EMIT_ROWS>(p, a, vec, warps);
+    launch_chain<F, EMIT_ROWS>(p, a, vec, warps, geo);
     prof_mark(p, 0);
   }
   else
   {
-    launch_chain<F, EMIT_NONE>(p, a, false, warps);
+    launch_chain<F, EMIT_NONE>(p, a, false, warps, geo);
   }
   CU_TRY(p, cudaGetLastError());
   p->hist_sel ^= 1;
@@ -1113,7 +1160,7 @@ bool do_roundtrip(Plan* p, size_t n, const T* in, T* out, const cx<F>* gains = n
   const T* x = stage_samples<T>(p, n, in, &ok);
   if (!ok) return false;
   const size_t ch = p->channels;
-  const unsigned groups = groups_for(p);
+  const unsigned max_groups = groups_for(p, GEO_NARROW);    // either geometry may be chosen per piece
   const bool out_dev = classify(out) == kDevice;
   T* y = out;
   if (!out_dev)
@@ -1123,10 +1170,11 @@ bool do_roundtrip(Plan* p, size_t n, const T* in, T* out, const cx<F>* gains = n
   }
   size_t piece = env_size("SDFT_B200_ROUNDTRIP_PIECE", (size_t)1 << 22);
   if (piece > n) piece = n;
-  if (!reserve(p, p->part, ch * groups * piece * sizeof(F))) return false;
+  if (!reserve(p, p->part, ch * max_groups * piece * sizeof(F))) return false;
   for (size_t t0 = 0; t0 < n; t0 += piece)
   {
     const size_t len = (t0 + piece <= n) ? piece : n - t0;
+    const unsigned groups = groups_for(p, choose_geo(p, len));   // what analysis_chained will use for this piece
     if (!analysis_chained<T, F>(p, len, x + t0, n, (cx<F>*)nullptr, 0, (F*)p->part.ptr, weights)) return false;
     size_t blocks = (len + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;

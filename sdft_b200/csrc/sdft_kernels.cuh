@@ -46,9 +46,14 @@ template <typename F> struct cx { F r, i; };
 /* Work geometry of the emit warps.  A lane owns CPL consecutive cells and stores them as 32-byte
  * groups of GROUP cells; the halo on either side of a warp is one group wide (>= the 2 cells the
  * Blackman taps need), which keeps every group store 32-byte aligned. */
-template <typename F> struct Geo;
-template <> struct Geo<double> { enum { CPL = 4, GROUP = 2, WC = 32 * 4 }; };
-template <> struct Geo<float>  { enum { CPL = 8, GROUP = 4, WC = 32 * 8 }; };
+enum { GEO_WIDE = 0, GEO_NARROW = 1 };
+template <typename F, int GEO> struct Geo;
+template <> struct Geo<double, GEO_WIDE>   { enum { CPL = 4, GROUP = 2, WC = 32 * 4 }; };
+template <> struct Geo<float, GEO_WIDE>    { enum { CPL = 8, GROUP = 4, WC = 32 * 8 }; };
+/* narrow warps (one 32-byte store group per lane) for short calls: twice the warps, half the work per
+ * time step each -- a short call is bound by the latency of its L sequential steps, not by bandwidth */
+template <> struct Geo<double, GEO_NARROW> { enum { CPL = 2, GROUP = 2, WC = 32 * 2 }; };
+template <> struct Geo<float, GEO_NARROW>  { enum { CPL = 4, GROUP = 4, WC = 32 * 4 }; };
 
 /* ------------------------------------------------------------------------------------------------
  * arithmetic policies (complex level)
@@ -471,7 +476,7 @@ __global__ void phase_at_kernel(const cx<F>* __restrict__ tw_ext, const cx<F>* _
  * Lane engine of the emit phase: replay a chunk from its carry, demodulate, apply the window across
  *     neighbouring cells and stream the (n, m) rows out.
  *
- *     One warp owns Geo<F>::WC consecutive cells (CPL per lane: 128 cells for double, 256 for float) of
+ *     One warp owns Geo<F, GEO>::WC consecutive cells (CPL per lane: 128 cells for double, 256 for float) of
  *     one chunk and is independent of every other warp: the outermost GROUP cells on either side are
  *     halo (recomputed by the neighbouring warp), so 124 (double) / 248 (float) bins per warp are
  *     stored; the boxcar window needs no halo.  Neighbour cells inside the warp come from registers
@@ -541,23 +546,23 @@ template <> struct StageOps<float, true>
   }
 };
 
-template <typename F, int WINDOW> struct EmitGeo
+template <typename F, int WINDOW, int GEO> struct EmitGeo
 {
   enum
   {
-    CPL = Geo<F>::CPL,
-    GROUP = Geo<F>::GROUP,
+    CPL = Geo<F, GEO>::CPL,
+    GROUP = Geo<F, GEO>::GROUP,
     NGROUP = CPL / GROUP,
-    WC = Geo<F>::WC,
+    WC = Geo<F, GEO>::WC,
     HALO = (WINDOW == 0) ? 0 : (int)GROUP,
     SPAN = WC - 2 * HALO        // bins stored per warp
   };
 };
 
-template <typename F, int WINDOW, bool VEC>
+template <typename F, int WINDOW, bool VEC, int GEO>
 struct EmitLane
 {
-  typedef EmitGeo<F, WINDOW> G;
+  typedef EmitGeo<F, WINDOW, GEO> G;
   cx<F> acc[G::CPL];
   cx<F> ph[G::CPL];
   cx<F> tw[G::CPL];
@@ -846,7 +851,7 @@ __global__ void synth_finish_kernel(const F* __restrict__ part, unsigned groups,
  * K23  single-pass chained scan + emit (the production analysis kernel)
  *
  *      Work decomposition.  Time is cut into chunks (make_schedule), bins into warp-wide groups of
- *      Geo<F>::WC cells.  One WARP owns one (chunk, group); one CTA owns `W` CONSECUTIVE CHUNKS of the
+ *      Geo<F, GEO>::WC cells.  One WARP owns one (chunk, group); one CTA owns `W` CONSECUTIVE CHUNKS of the
  *      same group of one channel (a "block item").  Per warp:
  *        A. the chunk's own total  sum_i P[c+i] delta_i  (FP only, no memory traffic);
  *        B. the carry: totals of the CTA's chunks meet in shared memory; warp 0 adds them up in chunk
@@ -896,8 +901,8 @@ template <typename F> struct ChainArgs
   const cx<F>* f0;         // (rows, cells)
   const cx<F>* acc_in;     // (channels, cells)
   cx<F>* acc_out;
-  cx<F>* totals;           // (channels, nblocks, groups, Geo<F>::WC) aggregate of each block item
-  cx<F>* prefix;           // (channels, nblocks, groups, Geo<F>::WC) inclusive prefix after each block item
+  cx<F>* totals;           // (channels, nblocks, groups, WC) aggregate of each block item
+  cx<F>* prefix;           // (channels, nblocks, groups, WC) inclusive prefix after each block item
   unsigned* flags;         // (channels, nblocks, groups): 2*epoch = aggregate published, 2*epoch+1 = prefix published
   unsigned* control;       // [0] ticket counter, [1] error flag
   unsigned epoch;
@@ -1060,12 +1065,12 @@ __device__ __forceinline__ void cp_async_wait_all()
  * The rows to add (prefix or acc_in, then the aggregates q+1 .. jb-1) are fetched into the shared-memory
  * staging area `stage` (`stage_rows` rows) with cp.async, as many at once as fit -- one memory round
  * trip for up to stage_rows rows instead of one per four -- and then added in order. */
-template <typename F>
+template <typename F, int GEO>
 __device__ __forceinline__ void look_back(const ChainArgs<F>& a, size_t item, size_t item_stride, unsigned jb, unsigned lane,
                                           const cx<F>* acc_in_cells, cx<F>* stage, unsigned stage_rows, cx<F>* acc,
                                           unsigned trace_slot)
 {
-  typedef Geo<F> G;
+  typedef Geo<F, GEO> G;
   typedef Arith<F> A;
   const unsigned code_total = a.epoch * 2u, code_prefix = a.epoch * 2u + 1u;
   long long top = (long long)jb - 1;
@@ -1155,10 +1160,10 @@ __device__ __forceinline__ void look_back(const ChainArgs<F>& a, size_t item, si
   }
 }
 
-template <typename F, int WINDOW, bool VEC, int EMIT, int MODE>
+template <typename F, int WINDOW, bool VEC, int EMIT, int MODE, int GEO>
 __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const ChainArgs<F> a)
 {
-  typedef EmitGeo<F, WINDOW> G;
+  typedef EmitGeo<F, WINDOW, GEO> G;
   typedef Arith<F> A;
   constexpr bool SLIDE = IsSlide<F, MODE>::value != 0;     // double fast mode
   constexpr bool FUSED = (MODE == MODE_FAST) && !SLIDE;     // float fused mode
@@ -1218,7 +1223,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   __syncwarp();
   SDFT_B200_STAMP(1);   // deltas in shared memory
 
-  EmitLane<F, WINDOW, VEC> L;
+  EmitLane<F, WINDOW, VEC, GEO> L;
   const int e0 = L.setup(group, lane, a.m);
   bool live[G::CPL];
   cx<F> zero;
@@ -1340,7 +1345,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
       cx<F> start[G::CPL];
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b) start[b] = carry[b];
-      look_back<F>(a, item, item_stride, jb, lane, start, sstage, a.stage_rows, carry, ticket);
+      look_back<F, GEO>(a, item, item_stride, jb, lane, start, sstage, a.stage_rows, carry, ticket);
     }
     SDFT_B200_STAMP(4);   // carry known
 #pragma unroll
@@ -1509,17 +1514,17 @@ SDFT_B200_PRAGMA_UNROLL(SDFT_B200_EMIT_UNROLL)
 #undef stot
 
 /* dynamic shared memory of one scan/emit CTA of `warps` warps and chunk length `chunk` */
-template <typename F>
+template <typename F, int GEO>
 inline size_t scan_smem_bytes(unsigned warps, unsigned chunk)
 {
-  return (size_t)warps * (chunk + kDeltaPad) * sizeof(F) + (size_t)(warps + 1) * Geo<F>::WC * sizeof(cx<F>);
+  return (size_t)warps * (chunk + kDeltaPad) * sizeof(F) + (size_t)(warps + 1) * Geo<F, GEO>::WC * sizeof(cx<F>);
 }
 /* rows of look-back staging that fit next to it under the 48 KiB a CTA gets without opting in */
-template <typename F>
+template <typename F, int GEO>
 inline unsigned scan_stage_rows(unsigned warps, unsigned chunk)
 {
-  const size_t row = Geo<F>::WC * sizeof(cx<F>);
-  const size_t base = scan_smem_bytes<F>(warps, chunk);
+  const size_t row = Geo<F, GEO>::WC * sizeof(cx<F>);
+  const size_t base = scan_smem_bytes<F, GEO>(warps, chunk);
   size_t rows = ((size_t)48 * 1024 - base) / row;
   if (rows > 16) rows = 16;
   if (rows < 2) rows = 2;
