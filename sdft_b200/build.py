@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsdft_b200.so")
 SOURCES = [os.path.join(CSRC, "sdft_b200.cu")]
-DEPENDS = SOURCES + [os.path.join(CSRC, "sdft_kernels.cuh"),
-                     os.path.join(HERE, "..", "include", "sdft_b200.h")]
+DEPENDS = SOURCES + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".hpp"))] + [
+    os.path.join(HERE, "..", "include", "sdft_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
