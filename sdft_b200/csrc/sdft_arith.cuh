@@ -91,49 +91,9 @@ __device__ __forceinline__ cx<float> pk_sub(cx<float> a, cx<float> b)
   return o;
 }
 
-__device__ __forceinline__ cx<float> pk_fma(cx<float> a, cx<float> b, cx<float> c)   // (a.r*b.r+c.r, a.i*b.i+c.i)
-{
-  cx<float> o;
-  asm("{.reg .b64 x, y, z, w; mov.b64 x, {%2, %3}; mov.b64 y, {%4, %5}; mov.b64 z, {%6, %7}; fma.rn.f32x2 w, x, y, z; mov.b64 {%0, %1}, w;}"
-      : "=f"(o.r), "=f"(o.i) : "f"(a.r), "f"(a.i), "f"(b.r), "f"(b.i), "f"(c.r), "f"(c.i));
-  return o;
-}
-__device__ __forceinline__ cx<float> pk_fma_s(cx<float> a, float k, cx<float> c)           // (a.r*k+c.r, a.i*k+c.i)
-{
-  cx<float> o;
-  asm("{.reg .b64 x, y, z, w; mov.b64 x, {%2, %3}; mov.b64 y, {%4, %4}; mov.b64 z, {%5, %6}; fma.rn.f32x2 w, x, y, z; mov.b64 {%0, %1}, w;}"
-      : "=f"(o.r), "=f"(o.i) : "f"(a.r), "f"(a.i), "f"(k), "f"(c.r), "f"(c.i));
-  return o;
-}
-
 template <> struct Arith<float>
 {
   typedef float F;
-  /* ---- fused variants (MODE_FAST): only used where the result is NOT fed back into the modulation
-   * phase.  The phase recurrence `rotate` stays un-fused in every mode: its rounding compounds over up
-   * to 2m-1 steps and must be the reference's bit for bit; a fused accumulate or a fused
-   * output stage moves a value by <= 1 ulp, the same order as the chunked summation order does. ---- */
-  static __device__ __forceinline__ cx<F> mac_fused(cx<F> acc, cx<F> p, F d) { return pk_fma_s(p, d, acc); }
-  static __device__ __forceinline__ cx<F> demod_fused(cx<F> a, cx<F> p)
-  {
-    /* (ar*pr + ai*pi, ai*pr - ar*pi) */
-    cx<F> sw, np;
-    sw.r = a.i; sw.i = a.r;
-    np.r = p.i; np.i = -p.i;
-    const cx<F> u = pk_mul(sw, np);          // (ai*pi, -ar*pi)
-    cx<F> pr;
-    pr.r = p.r; pr.i = p.r;
-    return pk_fma(a, pr, u);
-  }
-  template <int WINDOW>
-  static __device__ __forceinline__ cx<F> window_fused(cx<F> l2, cx<F> l1, cx<F> c, cx<F> r1, cx<F> r2, const WindowConst<F>& k)
-  {
-    if (WINDOW == 0) return pk_scale(c, k.c0);
-    const cx<F> s1 = pk_scale(pk_add(l1, r1), -k.c1);
-    cx<F> y = pk_fma_s(c, k.c0, s1);
-    if (WINDOW == 3) y = pk_fma_s(pk_add(l2, r2), k.c2, y);
-    return y;
-  }
   static __device__ __forceinline__ cx<F> cadd(cx<F> a, cx<F> b)
   {
     cx<F> o;

@@ -411,11 +411,9 @@ Plan* plan_create(size_t m, int window, double latency, size_t channels)
   if (p->forced_warps > (unsigned)kScanWarps) p->forced_warps = kScanWarps;
   {
     /* double frequency domain: fast (demodulated replay) unless SDFT_B200_F64=modulated.
-     * float: the reference's modulated scheme, every rounding kept (rows are bit-exact within a chunk).
-     * SDFT_B200_F32=fused fuses the accumulate / demodulate / window stages (FFMA2, ~5 % faster): the
-     * phase recurrence stays bit-exact, but rows that are pure cancellation noise (the first samples
-     * after a reset under a Blackman window) then carry OTHER noise than the reference's, which the
-     * per-call 1e-4 gate of the parity tests does not accept -- hence opt-in. */
+     * float: the reference's modulated scheme; the replay keeps every rounding of the reference (rows are
+     * bit-exact within a chunk); the chunk totals that feed the carries are summed in double on the FP64
+     * pipe unless SDFT_B200_F32=strict asks for the float recurrence there too */
     if (type_id<F>::value == kF64)
     {
       const char* md = getenv("SDFT_B200_F64");
@@ -424,7 +422,7 @@ Plan* plan_create(size_t m, int window, double latency, size_t channels)
     else
     {
       const char* md = getenv("SDFT_B200_F32");
-      p->mode = (md && !strcmp(md, "fused")) ? MODE_FAST : MODE_MODULATED;
+      p->mode = (md && !strcmp(md, "strict")) ? MODE_MODULATED : MODE_FAST;
     }
     p->prescale = (p->mode == MODE_FAST && type_id<F>::value == kF64) ? (double)make_window_const<double>(m, window).pre : 1.0;
   }
@@ -496,7 +494,7 @@ unsigned groups_for(const Plan* p, int geo = GEO_WIDE)
 constexpr double kNarrowBelow = 1.5e6;   // total wide warp-steps of a call below which narrow warps win (profiles/r01_geo_sweep.md)
 int choose_geo(const Plan* p, size_t n)
 {
-  const bool default_mode = (p->fd == kF64) ? (p->mode == MODE_FAST) : (p->mode == MODE_MODULATED);
+  const bool default_mode = (p->mode == MODE_FAST);
   if (!default_mode) return GEO_WIDE;
   if (p->forced_geo >= 0) return p->forced_geo;
   const double u = (double)n * (double)groups_for(p, GEO_WIDE) * (double)p->channels;
@@ -544,7 +542,7 @@ void launch_chain_geo(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps)
 {
   const dim3 grid(a.total_blocks);
   const size_t smem = scan_smem_bytes<F, GEO>(warps, a.sched.chunk) + (size_t)a.stage_rows * Geo<F, GEO>::WC * sizeof(cx<F>);
-  constexpr int kDefaultMode = (sizeof(F) == sizeof(double)) ? (int)MODE_FAST : (int)MODE_MODULATED;
+  constexpr int kDefaultMode = (int)MODE_FAST;
   /* programmatic dependent launch: the CTAs of this call may become resident while the previous kernel
    * of the stream drains; they wait at the top of the kernel (griddepcontrol.wait) until that kernel
    * has completed and flushed, so nothing else about the ordering changes.  Hides the launch latency

@@ -59,8 +59,7 @@ __device__ __forceinline__ cx<F> shfl_down1(cx<F> v)
   return o;
 }
 
-/* accumulate / demodulate / window stages of the modulated replay: the reference's own roundings, or
- * (float MODE_FAST) the fused forms */
+/* accumulate / demodulate / window stages of the modulated replay with the reference's own roundings */
 template <typename F, bool FUSED> struct StageOps
 {
   static __device__ __forceinline__ cx<F> mac(cx<F> acc, cx<F> p, F d) { return Arith<F>::mac(acc, p, d); }
@@ -71,18 +70,6 @@ template <typename F, bool FUSED> struct StageOps
     return Arith<F>::template window<WINDOW>(l2, l1, c, r1, r2, k);
   }
 };
-template <> struct StageOps<float, true>
-{
-  typedef float F;
-  static __device__ __forceinline__ cx<F> mac(cx<F> acc, cx<F> p, F d) { return Arith<F>::mac_fused(acc, p, d); }
-  static __device__ __forceinline__ cx<F> demod(cx<F> a, cx<F> p) { return Arith<F>::demod_fused(a, p); }
-  template <int WINDOW>
-  static __device__ __forceinline__ cx<F> window(cx<F> l2, cx<F> l1, cx<F> c, cx<F> r1, cx<F> r2, const WindowConst<F>& k)
-  {
-    return Arith<F>::template window_fused<WINDOW>(l2, l1, c, r1, r2, k);
-  }
-};
-
 template <typename F, int WINDOW, int GEO> struct EmitGeo
 {
   enum

@@ -329,7 +329,8 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   typedef EmitGeo<F, WINDOW, GEO> G;
   typedef Arith<F> A;
   constexpr bool SLIDE = IsSlide<F, MODE>::value != 0;     // double fast mode
-  constexpr bool FUSED = (MODE == MODE_FAST) && !SLIDE;     // float fused mode
+  constexpr bool FUSED = false;                             // stages keep the reference's roundings in every mode
+  constexpr bool DPTOTALS = (MODE == MODE_FAST) && !SLIDE;  // float fast mode: chunk totals on the FP64 pipe
   typedef StageOps<F, FUSED> S;
   /* dynamic shared memory, sized by the launch (scan_smem_bytes): deltas of the CTA's chunks, their
    * totals, the carry at the CTA's first chunk */
@@ -443,6 +444,37 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
         for (int b = 0; b < G::CPL; ++b) L.ph[b] = A::rotate(L.ph[b], L.tw[b]);
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b) tot[b] = X::cmul(L.ph[b], tot[b]);
+    }
+    else if constexpr (DPTOTALS)
+    {
+      /* float, fast mode: total = P_start * sum_i tw^i delta_i by Horner in DOUBLE.  The products of two
+       * floats are exact in double, so this is the chunk's sum with the float twiddle's own (systematic)
+       * error and without the float recurrence's per-step rounding noise -- closer to the exact sum than
+       * the reference's own float accumulation, off the strict replay by < 1e-6 of a term (the gate is
+       * 1e-4).  It moves the totals from the FP32 pipe, which bounds the float kernel, to the idle FP64
+       * pipe.  P_start is the bit-exact table phase; the replay (phase C) stays strict. */
+      cx<double> h[G::CPL], w[G::CPL];
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b)
+      {
+        h[b].r = 0.0; h[b].i = 0.0;
+        w[b].r = (double)L.tw[b].r; w[b].i = (double)L.tw[b].i;
+        L.ph[b] = live[b] ? phase_at<F>(a.f0, a.cells, e0 + b, cs.cursor0, L.tw[b]) : zero;
+      }
+#pragma unroll 2
+      for (int i = (int)cs.len - 1; i >= 0; --i)
+      {
+        const double d = (double)sdelta[i];
+#pragma unroll
+        for (int b = 0; b < G::CPL; ++b) h[b] = Arith<double>::horner(h[b], w[b], d);
+      }
+#pragma unroll
+      for (int b = 0; b < G::CPL; ++b)
+      {
+        const double pr = (double)L.ph[b].r, pi = (double)L.ph[b].i;
+        tot[b].r = (F)(pr * h[b].r - pi * h[b].i);
+        tot[b].i = (F)(pr * h[b].i + pi * h[b].r);
+      }
     }
     else
     {
