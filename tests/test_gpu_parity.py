@@ -149,6 +149,38 @@ def test_float_fast_totals_vs_strict(SDFT, window, monkeypatch):
         assert rel_err(fast.state()[2], o.state()[2]) <= 1e-5
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_randomized_plans_and_call_sequences(SDFT, seed, monkeypatch):
+    """Random plan shapes, launch geometries and call sequences against the oracle: exercises chunk
+    boundaries, period wraps inside and between calls, partial first chunks, both warp geometries, every
+    CTA width and chunk length, single- and multi-block chains."""
+    from oracle import Oracle
+    rng = np.random.default_rng(1000 + seed)
+    for trial in range(6):
+        td, fd = TYPES[int(rng.integers(4))]
+        window = ["boxcar", "hann", "hamming", "blackman"][int(rng.integers(4))]
+        latency = float(rng.choice([1.0, 0.5, 0.25]))
+        m = int(rng.choice([1, 2, 3, 5, 8, 31, 64, 100, 257, 600, 1000]))
+        monkeypatch.setenv("SDFT_B200_GEO", str(rng.choice(["wide", "narrow"])))
+        monkeypatch.setenv("SDFT_B200_WARPS", str(int(rng.choice([0, 1, 2, 3, 4, 8]))))
+        g = SDFT(m, window, latency, td=td, fd=fd)
+        chunk = int(rng.choice([0, 32, 64, 96, 128, 512]))
+        if chunk:
+            g.set_chunk(chunk)
+        o = Oracle(td, fd, m, window, latency)
+        for call in range(6):
+            kind = int(rng.integers(4))
+            n = [int(rng.integers(1, 10)), int(rng.integers(1, 2 * m + 2)), 2 * m + int(rng.integers(-3, 4)),
+                 int(rng.integers(2 * m, 6 * m + 50))][kind]
+            n = max(1, n)
+            x = rng.uniform(-1, 1, n)
+            want, got = o.sdft(x), g.sdft(x)
+            assert rel_err(got, want) <= TOL[fd], (seed, trial, call, td, fd, window, m, n, chunk, rel_err(got, want))
+        cg, hg, ag, _ = g.state()
+        co, ho, ao, _ = o.state()
+        assert cg == co and np.array_equal(_bits(hg), _bits(ho)) and rel_err(ag, ao) <= TOL[fd]
+
+
 def test_reset_and_getters(SDFT):
     from oracle import Oracle
     g = SDFT(16, "hamming", 0.5, td="f32", fd="f64")
