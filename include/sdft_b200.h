@@ -100,6 +100,11 @@ typedef struct sdft_b200_plan sdft_b200_plan_t;
    * materialises the (n, m) matrix; out[t] equals isdft(sdft(in[t])) */                                       \
   SDFT_B200_API void sdft_b200_##SFX##_roundtrip_n(sdft_b200_plan_t* plan, size_t nsamples, const TD* in,      \
                                                    TD* out);                                                   \
+  /* extension: SDFT.convolve of the reference's Python class (python/src/sdft/sdft.py:146-203): windows   \
+   * `nsamples` UN-windowed rows in the frequency domain, out = window(in) / dftsize, mirror cells as in   \
+   * sdft.h:589-595; stateless; in/out both (nsamples, dftsize), host or device */                          \
+  SDFT_B200_API void sdft_b200_##SFX##_convolve_n(sdft_b200_plan_t* plan, size_t nsamples, const FDX* in,      \
+                                                  FDX* out);                                                   \
   /* extension: the same with a spectral gain between analysis and synthesis: out[t] equals               \
    * isdft(gains .* sdft(in[t])), `gains` being dftsize complex factors (host or device memory) */            \
   SDFT_B200_API void sdft_b200_##SFX##_roundtrip_gain_n(sdft_b200_plan_t* plan, size_t nsamples, const TD* in, \

@@ -33,6 +33,7 @@ TYPED = {
     "isdft_batch": (_V, [_P, _SZ, _P, _P]),
     "roundtrip_n": (_V, [_P, _SZ, _P, _P]),
     "roundtrip_gain_n": (_V, [_P, _SZ, _P, _P, _P]),
+    "convolve_n": (_V, [_P, _SZ, _P, _P]),
 }
 UNTYPED = {
     "sdft_b200_last_error": (_I, [_P]),

@@ -1091,6 +1091,52 @@ bool do_roundtrip(Plan* p, size_t n, const T* in, T* out, const cx<F>* gains = n
   return true;
 }
 
+/* SDFT.convolve of the reference's Python class (python/src/sdft/sdft.py:146-203): window(rows) / m */
+template <typename F>
+bool do_convolve(Plan* p, size_t n, const cx<F>* in, cx<F>* out)
+{
+  if (n == 0) return true;
+  CU_TRY(p, cudaSetDevice(p->device));
+  const size_t m = p->m, ch = p->channels;
+  const int need = (p->window == 3) ? 3 : ((p->window == 0) ? 1 : 2);
+  if ((int)m < need)
+  {
+    plan_fail(p, SDFT_B200_ERR_ARG, "convolve: dftsize too small for this window", __FILE__, __LINE__);
+    return false;
+  }
+  const size_t bytes = ch * n * m * sizeof(cx<F>);
+  const bool in_dev = classify(in) == kDevice, out_dev = classify(out) == kDevice;
+  const cx<F>* src = in;
+  cx<F>* dst = out;
+  if (!in_dev)
+  {
+    if (!reserve(p, p->tile[0], bytes)) return false;
+    CU_TRY(p, cudaMemcpyAsync(p->tile[0].ptr, in, bytes, cudaMemcpyHostToDevice, p->stream));
+    src = (const cx<F>*)p->tile[0].ptr;
+  }
+  if (!out_dev)
+  {
+    if (!reserve(p, p->tile[1], bytes)) return false;
+    dst = (cx<F>*)p->tile[1].ptr;
+  }
+  const F scale = (F)1 / (F)m;
+  F c0 = scale, c1 = 0, c2 = 0;
+  if (p->window == 1) { c0 = (F)0.5 * scale; c1 = (F)0.25 * scale; }
+  if (p->window == 2) { c0 = (F)0.54 * scale; c1 = (F)0.23 * scale; }
+  if (p->window == 3) { c0 = (F)0.42 * scale; c1 = (F)0.25 * scale; c2 = (F)0.04 * scale; }
+  size_t blocks = (ch * n * m + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  convolve_kernel<F><<<(unsigned)blocks, 256, 0, p->stream>>>(src, dst, ch * n, (unsigned)m, p->window, c0, c1, c2);
+  p->launches++;
+  CU_TRY(p, cudaGetLastError());
+  if (!out_dev)
+  {
+    CU_TRY(p, cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+  }
+  return true;
+}
+
 template <typename T, typename F>
 bool typed(Plan* p, const char* fn)
 {
@@ -1170,6 +1216,10 @@ bool typed(Plan* p, const char* fn)
   extern "C" void sdft_b200_##SFX##_roundtrip_n(sdft_b200_plan_t* p, size_t n, const TD* in, TD* out)           \
   {                                                                                                             \
     if (typed<TD, FD>(p, "sdft_roundtrip_n: plan type mismatch")) do_roundtrip<TD, FD>(p, n, in, out);          \
+  }                                                                                                             \
+  extern "C" void sdft_b200_##SFX##_convolve_n(sdft_b200_plan_t* p, size_t n, const FDX* in, FDX* out)          \
+  {                                                                                                             \
+    if (typed<TD, FD>(p, "sdft_convolve_n: plan type mismatch")) do_convolve<FD>(p, n, (const cx<FD>*)in, (cx<FD>*)out); \
   }                                                                                                             \
   extern "C" void sdft_b200_##SFX##_roundtrip_gain_n(sdft_b200_plan_t* p, size_t n, const TD* in, TD* out,      \
                                                      const FDX* gains)                                          \

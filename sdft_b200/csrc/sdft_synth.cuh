@@ -146,4 +146,47 @@ __global__ void __launch_bounds__(kSynthWarps * 32) synth_kernel(const cx<F>* __
 }
 
 
+/* ------------------------------------------------------------------------------------------------
+ * Window a given (n, m) matrix of UN-windowed rows in the frequency domain: the stand-alone form of
+ * sdft_etc_convolve (sdft.h:350-402) that the reference's Python class exposes as SDFT.convolve
+ * (python/src/sdft/sdft.py:146-203), mirror cells included (below bin 0 about bin 0, above bin m-1 about
+ * bin m-1).  Stateless, one thread per bin, HBM-bound (reads and writes n*m complex values).
+ * c0/c1/c2 are the centre / first / second neighbour taps including the caller's scale.
+ * ---------------------------------------------------------------------------------------------- */
+template <typename F>
+__global__ void convolve_kernel(const cx<F>* __restrict__ in, cx<F>* __restrict__ out, unsigned long long n, unsigned m,
+                                int window, F c0, F c1, F c2)
+{
+  const unsigned long long total = n * m;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride)
+  {
+    const unsigned long long row = idx / m;
+    const int k = (int)(idx - row * m);
+    const cx<F>* r = in + row * m;
+    auto cell = [&](int j) -> cx<F>
+    {
+      cx<F> v;
+      if (j < 0) { v = r[-j]; v.i = -v.i; }                          // aux[-i] = conj(aux[+i])
+      else if (j >= (int)m) { v = r[2 * ((int)m - 1) - j]; v.i = -v.i; }   // aux[(m-1)+i] = conj(aux[(m-1)-i])
+      else v = r[j];
+      return v;
+    };
+    const cx<F> c = r[k];
+    cx<F> y;
+    y.r = c.r * c0; y.i = c.i * c0;
+    if (window != 0)
+    {
+      const cx<F> l1 = cell(k - 1), r1 = cell(k + 1);
+      y.r -= (l1.r + r1.r) * c1; y.i -= (l1.i + r1.i) * c1;
+      if (window == 3)
+      {
+        const cx<F> l2 = cell(k - 2), r2 = cell(k + 2);
+        y.r += (l2.r + r2.r) * c2; y.i += (l2.i + r2.i) * c2;
+      }
+    }
+    out[idx] = y;
+  }
+}
+
 }  // namespace sdftb200

@@ -198,6 +198,27 @@ class SDFT:
         call(x.shape[-1], x.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p))
         return y
 
+    def convolve(self, x):
+        """Window the specified DFT matrix (sdft.py:146-203): window(x) / bins, on the GPU."""
+        x = _device_view(x)
+        if _is_torch_cuda(x):
+            import torch
+            d = torch.atleast_2d(x).to(torch.complex64 if self.fd == "f32" else torch.complex128).contiguous()
+            assert d.shape[-1] == self.size, f'Expected (samples,frequencies), got {tuple(d.shape)}!'
+            out = torch.empty_like(d)
+            self._use_torch_stream()
+            self._f("convolve_n")(self._h, d.numel() // self.size // self.channels, ctypes.c_void_p(d.data_ptr()),
+                                  ctypes.c_void_p(out.data_ptr()))
+            self._check()
+            return out
+        d = np.ascontiguousarray(np.atleast_2d(x), dtype=_NP_FD[self.fd])
+        assert d.shape[-1] == self.size, f'Expected (samples,frequencies), got {d.shape}!'
+        out = np.empty_like(d)
+        self._f("convolve_n")(self._h, d.size // self.size // self.channels, d.ctypes.data_as(ctypes.c_void_p),
+                              out.ctypes.data_as(ctypes.c_void_p))
+        self._check()
+        return out
+
     def twiddles(self):
         a = np.empty(self.size, _NP_FD[self.fd])
         s = np.empty(self.size, _NP_FD[self.fd])

@@ -6,7 +6,8 @@ tree is mounted at /root/reference; the GPU box never executes this script.
 
 Sources of truth:
   * the reference's C header, compiled unmodified by oracle/Makefile (oracle.Ref)       -> c_ref_*.npz
-  * the reference's Python class python/src/sdft/sdft.py imported from /root/reference  -> py_ref.npz
+  * the reference's Python class python/src/sdft/sdft.py imported from /root/reference  -> py_ref.npz,
+                                                                                           py_convolve.npz
   * the reference's own integration-test input test/test.wav and test parameters
     (test/main.sh:3-6: DFTSIZE=1000 HOPSIZE=100 hann latency 1; BASELINE.json config 1: m=1024)
                                                                                           -> testwav.npz
@@ -109,6 +110,21 @@ def python_cases():
     print("py_ref.npz:", idx, "cases")
 
 
+def python_convolve_cases():
+    """SDFT.convolve of the reference's Python class on random un-windowed matrices -> py_convolve.npz"""
+    sys.path.insert(0, os.path.join(REF, "python", "src"))
+    from sdft import SDFT
+    rng = np.random.default_rng(0x5DF9)
+    out = {}
+    for m in (8, 37):
+        x = rng.uniform(-1, 1, (6, m)) + 1j * rng.uniform(-1, 1, (6, m))
+        out["x_m%d" % m] = x
+        for window in ("boxcar", "hann", "hamming", "blackman"):
+            out["y_m%d_%s" % (m, window)] = SDFT(m, window, 1).convolve(x)
+    np.savez_compressed(os.path.join(HERE, "py_convolve.npz"), **out)
+    print("py_convolve.npz written")
+
+
 def testwav_cases():
     pcm, sr = read_pcm24(os.path.join(REF, "test", "test.wav"))
     sha = hashlib.sha256(open(os.path.join(REF, "test", "test.wav"), "rb").read()).hexdigest()
@@ -157,4 +173,5 @@ if __name__ == "__main__":
     small_cases()
     table_cases()
     python_cases()
+    python_convolve_cases()
     testwav_cases()

@@ -258,6 +258,25 @@ def test_device_pointers_and_batch(SDFT):
     assert rel_err(got2, got) <= 1e-13   # one 3000-sample call vs three calls: other chunking, same rows
 
 
+@pytest.mark.parametrize("fd", ["f32", "f64"])
+def test_convolve_matches_reference_python_class(SDFT, fd, golden_dir):
+    """SDFT.convolve (python/src/sdft/sdft.py:146-203) against vectors produced by the reference's own
+    Python class (tests/golden/make_golden.py), host and device inputs."""
+    import torch
+    g = np.load(os.path.join(golden_dir, "py_convolve.npz"))
+    tol = 1e-13 if fd == "f64" else 1e-6
+    for m in (8, 37):
+        x = g["x_m%d" % m]
+        for window in ("boxcar", "hann", "hamming", "blackman"):
+            want = g["y_m%d_%s" % (m, window)]
+            plan = SDFT(m, window, 1, td="f32", fd=fd)
+            got = plan.convolve(x)
+            assert got.shape == want.shape
+            assert np.abs(got - want).max() <= tol * np.abs(want).max(), (m, window)
+            got_dev = plan.convolve(torch.from_numpy(x).cuda()).cpu().numpy()
+            assert np.array_equal(_bits(got_dev), _bits(got))
+
+
 def test_cuda_array_interface_inputs(SDFT):
     """Anything that exposes __cuda_array_interface__ is taken zero-copy (CuPy, Numba, ...)."""
     import torch
