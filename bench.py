@@ -315,6 +315,22 @@ def other_configs(torch, SDFT, scratch, peak):
     return res
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pins this rank to the CPU cores next to its GPU (NVML's affinity mask), so that the pinned host
+    buffers of the e2e legs are first-touched on the NUMA node the GPU's PCIe link hangs off."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, bits in enumerate(mask) for b in range(64) if (bits >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
@@ -331,6 +347,8 @@ def run_b200_arm(args, rank, local_rank, world):
     os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -543,6 +561,7 @@ def run_b200_arm(args, rank, local_rank, world):
     # ---- CPU baseline beside it (rank 0, N = 1) -----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, all_cpus)          # the CPU baseline gets every host core again
         threads = os.cpu_count() or 1
         spw = 4096
         agg, per_step, kind, single = cpu_reference_run(spw, threads, 2, 1)
