@@ -1,0 +1,429 @@
+/*
+ * sdft_calls.hpp -- host/device pointer plumbing of the entry points: tiling, pinned staging for pageable buffers, row-pointer variants, fused round trip, convolve.
+ * Host side of libsdft_b200.so; included by sdft_b200.cu only (one translation unit).
+ */
+#pragma once
+
+#include "sdft_launch.hpp"
+
+namespace
+{
+
+/* ------------------------------------------------------------------------------------------------
+ * host/device pointer plumbing
+ * ---------------------------------------------------------------------------------------------- */
+size_t tile_rows(const Plan* p, size_t n, size_t row_bytes)
+{
+  size_t rows = p->tile_bytes / (row_bytes * p->channels);
+  if (rows < 1) rows = 1;
+  if (rows > n) rows = n;
+  return rows;
+}
+
+/* samples -> device (no-op for device pointers).  Layout (channels, n). */
+template <typename T>
+const T* stage_samples(Plan* p, size_t n, const T* samples, bool* ok)
+{
+  *ok = true;
+  if (classify(samples) == kDevice) return samples;
+  const size_t bytes = p->channels * n * sizeof(T);
+  if (!reserve(p, p->samples, bytes)) { *ok = false; return nullptr; }
+  if (cudaMemcpyAsync(p->samples.ptr, samples, bytes, cudaMemcpyHostToDevice, p->stream) != cudaSuccess)
+  {
+    plan_fail(p, (int)cudaGetLastError(), "H2D samples", __FILE__, __LINE__);
+    *ok = false;
+    return nullptr;
+  }
+  return (const T*)p->samples.ptr;
+}
+
+template <typename T, typename F>
+bool do_sdft(Plan* p, size_t n, const T* samples, cx<F>* dfts)
+{
+  if (n == 0) return true;
+  CU_TRY(p, cudaSetDevice(p->device));
+  bool ok = true;
+  const T* x = stage_samples<T>(p, n, samples, &ok);
+  if (!ok) return false;
+  const size_t m = p->m, ch = p->channels;
+
+  if (classify(dfts) == kDevice)
+  {
+    return analysis_device<T, F>(p, n, x, n, dfts, n * m);
+  }
+
+  /* host destination: compute row tiles on the device and stream them out, overlapping the
+   * device-to-host copy of tile i with the kernels of tile i+1 */
+  const size_t row_bytes = m * sizeof(cx<F>);
+  const size_t rows = tile_rows(p, n, row_bytes);
+  const size_t ntiles = (n + rows - 1) / rows;
+  for (int b = 0; b < 2; ++b)
+    if (!reserve(p, p->tile[b], ch * rows * row_bytes)) return false;
+
+  auto compute = [&](size_t i) -> bool
+  {
+    const int b = (int)(i & 1);
+    const size_t t0 = i * rows;
+    const size_t len = (t0 + rows <= n) ? rows : n - t0;
+    if (i >= 2) CU_TRY(p, cudaStreamWaitEvent(p->stream, p->tile_free[b], 0));
+    if (!analysis_device<T, F>(p, len, x + t0, n, (cx<F>*)p->tile[b].ptr, len * m)) return false;
+    CU_TRY(p, cudaEventRecord(p->tile_ready[b], p->stream));
+    return true;
+  };
+  if (!compute(0)) return false;
+  if (classify(dfts) == kHostPageable && !p->driver_pageable)
+  {
+    /* device tile -> pinned staging (DMA) -> caller's pages (host threads); see HostCopier */
+    for (int b = 0; b < 2; ++b)
+      if (!reserve_stage(p, b, ch * rows * row_bytes)) return false;
+    auto dma = [&](size_t i) -> bool
+    {
+      const int b = (int)(i & 1);
+      const size_t t0 = i * rows;
+      const size_t len = (t0 + rows <= n) ? rows : n - t0;
+      CU_TRY(p, cudaStreamWaitEvent(p->copy_stream, p->tile_ready[b], 0));
+      CU_TRY(p, cudaMemcpyAsync(p->stage[b], p->tile[b].ptr, ch * len * row_bytes, cudaMemcpyDeviceToHost, p->copy_stream));
+      CU_TRY(p, cudaEventRecord(p->tile_free[b], p->copy_stream));
+      CU_TRY(p, cudaEventRecord(p->stage_done[b], p->copy_stream));
+      return true;
+    };
+    if (!dma(0)) return false;
+    std::vector<CopySeg> segs;
+    for (size_t i = 0; i < ntiles; ++i)
+    {
+      const int b = (int)(i & 1);
+      const size_t t0 = i * rows;
+      const size_t len = (t0 + rows <= n) ? rows : n - t0;
+      if (i + 1 < ntiles)
+      {
+        if (!compute(i + 1)) return false;    // its staging buffer was emptied by the host copy of tile i-1
+        if (!dma(i + 1)) return false;
+      }
+      CU_TRY(p, cudaEventSynchronize(p->stage_done[b]));
+      segs.clear();
+      for (size_t c = 0; c < ch; ++c)
+        segs.push_back({ dfts + (c * n + t0) * m, (const cx<F>*)p->stage[b] + c * len * m, len * row_bytes });
+      HostCopier::get().run(segs);
+    }
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    return true;
+  }
+  for (size_t i = 0; i < ntiles; ++i)
+  {
+    if (i + 1 < ntiles && !compute(i + 1)) return false;
+    const int b = (int)(i & 1);
+    const size_t t0 = i * rows;
+    const size_t len = (t0 + rows <= n) ? rows : n - t0;
+    CU_TRY(p, cudaStreamWaitEvent(p->copy_stream, p->tile_ready[b], 0));
+    for (size_t c = 0; c < ch; ++c)
+    {
+      CU_TRY(p, cudaMemcpyAsync(dfts + (c * n + t0) * m, (cx<F>*)p->tile[b].ptr + c * len * m, len * row_bytes,
+                                cudaMemcpyDeviceToHost, p->copy_stream));
+    }
+    CU_TRY(p, cudaEventRecord(p->tile_free[b], p->copy_stream));
+  }
+  CU_TRY(p, cudaStreamSynchronize(p->copy_stream));
+  CU_TRY(p, cudaStreamSynchronize(p->stream));
+  return true;
+}
+
+template <typename T, typename F>
+bool do_advance(Plan* p, size_t n, const T* samples)
+{
+  if (n == 0) return true;
+  CU_TRY(p, cudaSetDevice(p->device));
+  bool ok = true;
+  const bool host = classify(samples) != kDevice;
+  const T* x = stage_samples<T>(p, n, samples, &ok);
+  if (!ok) return false;
+  if (!analysis_device<T, F>(p, n, x, n, (cx<F>*)nullptr, 0)) return false;
+  if (host) CU_TRY(p, cudaStreamSynchronize(p->stream));
+  return true;
+}
+
+template <typename T, typename F>
+bool do_isdft(Plan* p, size_t n, const cx<F>* dfts, T* samples)
+{
+  if (n == 0) return true;
+  CU_TRY(p, cudaSetDevice(p->device));
+  const size_t m = p->m, ch = p->channels;
+  const bool out_dev = classify(samples) == kDevice;
+  T* y = samples;
+  if (!out_dev)
+  {
+    if (!reserve(p, p->synth_out, ch * n * sizeof(T))) return false;
+    y = (T*)p->synth_out.ptr;
+  }
+
+  if (classify(dfts) == kDevice)
+  {
+    if (!synthesis_device<T, F>(p, n, dfts, n * m, y, n)) return false;
+  }
+  else
+  {
+    const size_t row_bytes = m * sizeof(cx<F>);
+    const size_t rows = tile_rows(p, n, row_bytes);
+    const size_t ntiles = (n + rows - 1) / rows;
+    for (int b = 0; b < 2; ++b)
+      if (!reserve(p, p->tile[b], ch * rows * row_bytes)) return false;
+    auto upload = [&](size_t i) -> bool
+    {
+      const int b = (int)(i & 1);
+      const size_t t0 = i * rows;
+      const size_t len = (t0 + rows <= n) ? rows : n - t0;
+      if (i >= 2) CU_TRY(p, cudaStreamWaitEvent(p->copy_stream, p->tile_free[b], 0));
+      for (size_t c = 0; c < ch; ++c)
+      {
+        CU_TRY(p, cudaMemcpyAsync((cx<F>*)p->tile[b].ptr + c * len * m, dfts + (c * n + t0) * m, len * row_bytes,
+                                  cudaMemcpyHostToDevice, p->copy_stream));
+      }
+      CU_TRY(p, cudaEventRecord(p->tile_ready[b], p->copy_stream));
+      return true;
+    };
+    /* make sure earlier work on the compute stream that used the tiles is done */
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    if (classify(dfts) == kHostPageable && !p->driver_pageable)
+    {
+      /* caller's pages -> pinned staging (host threads) -> device tile (DMA); see HostCopier */
+      for (int b = 0; b < 2; ++b)
+        if (!reserve_stage(p, b, ch * rows * row_bytes)) return false;
+      std::vector<CopySeg> segs;
+      auto fill = [&](size_t i)
+      {
+        const int b = (int)(i & 1);
+        const size_t t0 = i * rows;
+        const size_t len = (t0 + rows <= n) ? rows : n - t0;
+        segs.clear();
+        for (size_t c = 0; c < ch; ++c)
+          segs.push_back({ (cx<F>*)p->stage[b] + c * len * m, dfts + (c * n + t0) * m, len * row_bytes });
+        HostCopier::get().run(segs);
+      };
+      fill(0);
+      for (size_t i = 0; i < ntiles; ++i)
+      {
+        const int b = (int)(i & 1);
+        const size_t t0 = i * rows;
+        const size_t len = (t0 + rows <= n) ? rows : n - t0;
+        if (i >= 2) CU_TRY(p, cudaStreamWaitEvent(p->copy_stream, p->tile_free[b], 0));
+        CU_TRY(p, cudaMemcpyAsync(p->tile[b].ptr, p->stage[b], ch * len * row_bytes, cudaMemcpyHostToDevice, p->copy_stream));
+        CU_TRY(p, cudaEventRecord(p->tile_ready[b], p->copy_stream));
+        CU_TRY(p, cudaEventRecord(p->stage_done[b], p->copy_stream));
+        if (i + 1 < ntiles)
+        {
+          if (i >= 1) CU_TRY(p, cudaEventSynchronize(p->stage_done[b ^ 1]));   // its previous upload has left the buffer
+          fill(i + 1);
+        }
+        CU_TRY(p, cudaStreamWaitEvent(p->stream, p->tile_ready[b], 0));
+        if (!synthesis_device<T, F>(p, len, (const cx<F>*)p->tile[b].ptr, len * m, y + t0, n)) return false;
+        CU_TRY(p, cudaEventRecord(p->tile_free[b], p->stream));
+      }
+    }
+    else
+    {
+    if (!upload(0)) return false;
+    for (size_t i = 0; i < ntiles; ++i)
+    {
+      if (i + 1 < ntiles && !upload(i + 1)) return false;
+      const int b = (int)(i & 1);
+      const size_t t0 = i * rows;
+      const size_t len = (t0 + rows <= n) ? rows : n - t0;
+      CU_TRY(p, cudaStreamWaitEvent(p->stream, p->tile_ready[b], 0));
+      if (!synthesis_device<T, F>(p, len, (const cx<F>*)p->tile[b].ptr, len * m, y + t0, n)) return false;
+      CU_TRY(p, cudaEventRecord(p->tile_free[b], p->stream));
+    }
+    }
+  }
+  if (!out_dev)
+  {
+    CU_TRY(p, cudaMemcpyAsync(samples, y, ch * n * sizeof(T), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+  }
+  return true;
+}
+
+/* row-pointer variants (sdft.h:622-628, 681-687): rows may be host or device pointers */
+template <typename T, typename F>
+bool do_sdft_nd(Plan* p, size_t n, const T* samples, cx<F>** rows_out)
+{
+  if (n == 0) return true;
+  if (p->channels != 1) { plan_fail(p, SDFT_B200_ERR_ARG, "sdft_nd on a batch plan", __FILE__, __LINE__); return false; }
+  CU_TRY(p, cudaSetDevice(p->device));
+  bool ok = true;
+  const T* x = stage_samples<T>(p, n, samples, &ok);
+  if (!ok) return false;
+  const size_t m = p->m, row_bytes = m * sizeof(cx<F>);
+  const size_t rows = tile_rows(p, n, row_bytes);
+  if (!reserve(p, p->tile[0], rows * row_bytes)) return false;
+  for (size_t t0 = 0; t0 < n; t0 += rows)
+  {
+    const size_t len = (t0 + rows <= n) ? rows : n - t0;
+    if (!analysis_device<T, F>(p, len, x + t0, n, (cx<F>*)p->tile[0].ptr, len * m)) return false;
+    for (size_t i = 0; i < len; ++i)
+    {
+      CU_TRY(p, cudaMemcpyAsync(rows_out[t0 + i], (cx<F>*)p->tile[0].ptr + i * m, row_bytes, cudaMemcpyDefault, p->stream));
+    }
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+  }
+  return true;
+}
+
+template <typename T, typename F>
+bool do_isdft_nd(Plan* p, size_t n, const cx<F>** rows_in, T* samples)
+{
+  if (n == 0) return true;
+  if (p->channels != 1) { plan_fail(p, SDFT_B200_ERR_ARG, "isdft_nd on a batch plan", __FILE__, __LINE__); return false; }
+  CU_TRY(p, cudaSetDevice(p->device));
+  const size_t m = p->m, row_bytes = m * sizeof(cx<F>);
+  const size_t rows = tile_rows(p, n, row_bytes);
+  if (!reserve(p, p->tile[0], rows * row_bytes)) return false;
+  const bool out_dev = classify(samples) == kDevice;
+  T* y = samples;
+  if (!out_dev)
+  {
+    if (!reserve(p, p->synth_out, n * sizeof(T))) return false;
+    y = (T*)p->synth_out.ptr;
+  }
+  for (size_t t0 = 0; t0 < n; t0 += rows)
+  {
+    const size_t len = (t0 + rows <= n) ? rows : n - t0;
+    for (size_t i = 0; i < len; ++i)
+    {
+      CU_TRY(p, cudaMemcpyAsync((cx<F>*)p->tile[0].ptr + i * m, rows_in[t0 + i], row_bytes, cudaMemcpyDefault, p->stream));
+    }
+    if (!synthesis_device<T, F>(p, len, (const cx<F>*)p->tile[0].ptr, len * m, y + t0, n)) return false;
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+  }
+  if (!out_dev)
+  {
+    CU_TRY(p, cudaMemcpyAsync(samples, y, n * sizeof(T), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+  }
+  return true;
+}
+
+/* analysis -> synthesis in ONE kernel: the rows never exist in memory.  Every warp weighs and reduces
+ * its bins per time step (SynthLane), per-group partial sums go to a scratch buffer and a small second
+ * kernel adds the groups in order.  Long calls are cut into pieces that bound the scratch. */
+template <typename T, typename F>
+bool do_roundtrip(Plan* p, size_t n, const T* in, T* out, const cx<F>* gains = nullptr)
+{
+  if (n == 0) return true;
+  CU_TRY(p, cudaSetDevice(p->device));
+  const cx<F>* weights = nullptr;
+  if (gains)
+  {
+    /* spectral processing between analysis and synthesis: every row is multiplied bin by bin with
+     * `gains` before sdft_isdft sees it, i.e. the synthesis weights become gains[k] * tws[k]
+     * (gains[k] * (-1)^k for latency 1, sdft.h:639-652) */
+    const size_t m = p->m;
+    std::vector<cx<F>> g(m), w(m);
+    if (classify(gains) == kDevice) CU_TRY(p, cudaMemcpy(g.data(), gains, m * sizeof(cx<F>), cudaMemcpyDeviceToHost));
+    else memcpy(g.data(), gains, m * sizeof(cx<F>));
+    std::vector<cx<F>> tw, tws;
+    make_tables<F>(m, p->latency, tw, tws);
+    for (size_t k = 0; k < m; ++k)
+    {
+      cx<F> t = tws[k];
+      if (p->latency == 1) { t.r = (k & 1) ? (F)(-1) : (F)(1); t.i = (F)0; }
+      w[k].r = g[k].r * t.r - g[k].i * t.i;
+      w[k].i = g[k].r * t.i + g[k].i * t.r;
+    }
+    if (!reserve(p, p->weights, m * sizeof(cx<F>))) return false;
+    CU_TRY(p, cudaMemcpyAsync(p->weights.ptr, w.data(), m * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(p, cudaStreamSynchronize(p->stream));   // w goes out of scope
+    weights = (const cx<F>*)p->weights.ptr;
+  }
+  bool ok = true;
+  const T* x = stage_samples<T>(p, n, in, &ok);
+  if (!ok) return false;
+  const size_t ch = p->channels;
+  const unsigned max_groups = groups_for(p, GEO_NARROW);    // either geometry may be chosen per piece
+  const bool out_dev = classify(out) == kDevice;
+  T* y = out;
+  if (!out_dev)
+  {
+    if (!reserve(p, p->synth_out, ch * n * sizeof(T))) return false;
+    y = (T*)p->synth_out.ptr;
+  }
+  size_t piece = env_size("SDFT_B200_ROUNDTRIP_PIECE", (size_t)1 << 22);
+  if (piece > n) piece = n;
+  if (!reserve(p, p->part, ch * max_groups * piece * sizeof(F))) return false;
+  for (size_t t0 = 0; t0 < n; t0 += piece)
+  {
+    const size_t len = (t0 + piece <= n) ? piece : n - t0;
+    const unsigned groups = groups_for(p, choose_geo(p, len));   // what analysis_chained will use for this piece
+    if (!analysis_chained<T, F>(p, len, x + t0, n, (cx<F>*)nullptr, 0, (F*)p->part.ptr, weights)) return false;
+    size_t blocks = (len + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    synth_finish_kernel<T, F><<<dim3((unsigned)blocks, (unsigned)ch), 256, 0, p->stream>>>(
+        (const F*)p->part.ptr, groups, len, y + t0, n);
+    p->launches++;
+    CU_TRY(p, cudaGetLastError());
+  }
+  if (!out_dev)
+  {
+    CU_TRY(p, cudaMemcpyAsync(out, y, ch * n * sizeof(T), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+  }
+  return true;
+}
+
+/* SDFT.convolve of the reference's Python class (python/src/sdft/sdft.py:146-203): window(rows) / m */
+template <typename F>
+bool do_convolve(Plan* p, size_t n, const cx<F>* in, cx<F>* out)
+{
+  if (n == 0) return true;
+  CU_TRY(p, cudaSetDevice(p->device));
+  const size_t m = p->m, ch = p->channels;
+  const int need = (p->window == 3) ? 3 : ((p->window == 0) ? 1 : 2);
+  if ((int)m < need)
+  {
+    plan_fail(p, SDFT_B200_ERR_ARG, "convolve: dftsize too small for this window", __FILE__, __LINE__);
+    return false;
+  }
+  const size_t bytes = ch * n * m * sizeof(cx<F>);
+  const bool in_dev = classify(in) == kDevice, out_dev = classify(out) == kDevice;
+  const cx<F>* src = in;
+  cx<F>* dst = out;
+  if (!in_dev)
+  {
+    if (!reserve(p, p->tile[0], bytes)) return false;
+    CU_TRY(p, cudaMemcpyAsync(p->tile[0].ptr, in, bytes, cudaMemcpyHostToDevice, p->stream));
+    src = (const cx<F>*)p->tile[0].ptr;
+  }
+  if (!out_dev)
+  {
+    if (!reserve(p, p->tile[1], bytes)) return false;
+    dst = (cx<F>*)p->tile[1].ptr;
+  }
+  const F scale = (F)1 / (F)m;
+  F c0 = scale, c1 = 0, c2 = 0;
+  if (p->window == 1) { c0 = (F)0.5 * scale; c1 = (F)0.25 * scale; }
+  if (p->window == 2) { c0 = (F)0.54 * scale; c1 = (F)0.23 * scale; }
+  if (p->window == 3) { c0 = (F)0.42 * scale; c1 = (F)0.25 * scale; c2 = (F)0.04 * scale; }
+  size_t blocks = (ch * n * m + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  convolve_kernel<F><<<(unsigned)blocks, 256, 0, p->stream>>>(src, dst, ch * n, (unsigned)m, p->window, c0, c1, c2);
+  p->launches++;
+  CU_TRY(p, cudaGetLastError());
+  if (!out_dev)
+  {
+    CU_TRY(p, cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+  }
+  return true;
+}
+
+template <typename T, typename F>
+bool typed(Plan* p, const char* fn)
+{
+  if (!p) return false;
+  if (p->td != type_id<T>::value || p->fd != type_id<F>::value)
+  {
+    plan_fail(p, SDFT_B200_ERR_TYPE, fn, __FILE__, __LINE__);
+    return false;
+  }
+  return true;
+}
+
+}  // namespace

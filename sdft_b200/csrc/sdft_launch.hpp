@@ -1,0 +1,286 @@
+/*
+ * sdft_launch.hpp -- per-call launch geometry (chunk length, CTA width, warp geometry) and the device-side passes: analysis_chained, synthesis_device.
+ * Host side of libsdft_b200.so; included by sdft_b200.cu only (one translation unit).
+ */
+#pragma once
+
+#include "sdft_plan.hpp"
+
+namespace
+{
+
+/* ------------------------------------------------------------------------------------------------
+ * device-side passes
+ * ---------------------------------------------------------------------------------------------- */
+void prof_mark(Plan* p, int which)
+{
+  if (!p->profiling) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaEventRecord(e, p->stream);
+  p->prof_events[which].push_back(e);
+}
+
+/* warp-wide groups of bins the plan's m bins are cut into, for either warp geometry */
+unsigned groups_for(const Plan* p, int geo = GEO_WIDE)
+{
+  unsigned wc, halo;
+  if (p->fd == kF32)
+  {
+    wc = geo == GEO_WIDE ? (unsigned)Geo<float, GEO_WIDE>::WC : (unsigned)Geo<float, GEO_NARROW>::WC;
+    halo = (unsigned)Geo<float, GEO_WIDE>::GROUP;
+  }
+  else
+  {
+    wc = geo == GEO_WIDE ? (unsigned)Geo<double, GEO_WIDE>::WC : (unsigned)Geo<double, GEO_NARROW>::WC;
+    halo = (unsigned)Geo<double, GEO_WIDE>::GROUP;
+  }
+  if (p->window == 0) halo = 0;
+  const unsigned span = wc - 2 * halo;
+  return (unsigned)((p->m + span - 1) / span);
+}
+
+/* narrow warps for short calls (see Geo<F, GEO_NARROW>); only the default arithmetic modes carry
+ * narrow kernels */
+constexpr double kNarrowBelow = 1.5e6;   // total wide warp-steps of a call below which narrow warps win (profiles/r01_geo_sweep.md)
+int choose_geo(const Plan* p, size_t n)
+{
+  const bool default_mode = (p->mode == MODE_FAST);
+  if (!default_mode) return GEO_WIDE;
+  if (p->forced_geo >= 0) return p->forced_geo;
+  const double u = (double)n * (double)groups_for(p, GEO_WIDE) * (double)p->channels;
+  return u < kNarrowBelow ? GEO_NARROW : GEO_WIDE;
+}
+
+/* 32-byte group stores need rows that start on a 32-byte boundary */
+template <typename F>
+bool can_vectorize(size_t m, const void* out, size_t out_stride)
+{
+  const size_t g = Geo<F, GEO_WIDE>::GROUP;
+  return (m % g == 0) && (((uintptr_t)out) % 32 == 0) && (out_stride % g == 0);
+}
+
+unsigned choose_chunk(const Plan* p, size_t n, int geo)
+{
+  if (p->forced_chunk)
+  {
+    size_t c = (p->forced_chunk / kF0Stride) * kF0Stride;
+    if (c < (size_t)kF0Stride) c = kF0Stride;
+    if (c > (size_t)kMaxChunk) c = kMaxChunk;
+    return (unsigned)c;
+  }
+  /* Measured on B200 (tools/chunk_sweep.py, profiles/r01_chunk_sweep.md): the best chunk length is a
+   * function of the call's total warp-steps U = samples x groups x channels.  Short chunks expose the
+   * per-chunk latencies (ticket, table loads, look-back), long chunks leave SMs without work. */
+  const double u = (double)n * (double)groups_for(p, GEO_WIDE) * (double)p->channels;
+  if (geo == GEO_NARROW)
+  {
+    /* profiles/r01_geo_sweep.md: narrow warps like longer chunks earlier, but never so long that a chain
+     * has fewer than 16 chunks */
+    unsigned c = (u < 16384.0) ? 32u : ((u < 30.0e3) ? 64u : 128u);
+    while (c > 32u && (size_t)c * 16 > n) c >>= 1;
+    return c;
+  }
+  if (u < 16384.0) return 32;
+  if (u < 100.0e3) return 64;
+  if (u < 4.0e6) return 128;
+  if (u < 16.0e6) return 256;
+  return kAutoChunk;
+}
+
+template <typename F, int EMIT, int GEO>
+void launch_chain_geo(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps)
+{
+  const dim3 grid(a.total_blocks);
+  const size_t smem = scan_smem_bytes<F, GEO>(warps, a.sched.chunk) + (size_t)a.stage_rows * Geo<F, GEO>::WC * sizeof(cx<F>);
+  constexpr int kDefaultMode = (int)MODE_FAST;
+  /* programmatic dependent launch: the CTAs of this call may become resident while the previous kernel
+   * of the stream drains; they wait at the top of the kernel (griddepcontrol.wait) until that kernel
+   * has completed and flushed, so nothing else about the ordering changes.  Hides the launch latency
+   * between back-to-back calls (streaming). */
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = p->pdl ? 1 : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(warps * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = p->stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define SDFT_CHAIN_CASE(W, MODE)                                                                       \
+  case W:                                                                                              \
+    if (vec) cudaLaunchKernelEx(&cfg, scan_emit_kernel<F, W, true, EMIT, MODE, GEO>, a);               \
+    else cudaLaunchKernelEx(&cfg, scan_emit_kernel<F, W, false, EMIT, MODE, GEO>, a);                  \
+    break;
+  if (GEO == GEO_NARROW || p->mode == kDefaultMode)
+  {
+    /* the narrow geometry exists for the default mode only (choose_geo) */
+    switch (p->window)
+    {
+      SDFT_CHAIN_CASE(0, kDefaultMode)
+      SDFT_CHAIN_CASE(1, kDefaultMode)
+      SDFT_CHAIN_CASE(2, kDefaultMode)
+      SDFT_CHAIN_CASE(3, kDefaultMode)
+    }
+  }
+  else if constexpr (GEO == GEO_WIDE)
+  {
+    constexpr int kOtherMode = (kDefaultMode == (int)MODE_FAST) ? (int)MODE_MODULATED : (int)MODE_FAST;
+    switch (p->window)
+    {
+      SDFT_CHAIN_CASE(0, kOtherMode)
+      SDFT_CHAIN_CASE(1, kOtherMode)
+      SDFT_CHAIN_CASE(2, kOtherMode)
+      SDFT_CHAIN_CASE(3, kOtherMode)
+    }
+  }
+#undef SDFT_CHAIN_CASE
+  p->launches++;
+}
+
+template <typename F, int EMIT>
+void launch_chain(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps, int geo)
+{
+  if (geo == GEO_NARROW) launch_chain_geo<F, EMIT, GEO_NARROW>(p, a, vec, warps);
+  else launch_chain_geo<F, EMIT, GEO_WIDE>(p, a, vec, warps);
+}
+
+/* warps (= consecutive chunks) per scan/emit CTA */
+unsigned scan_warps_for(const Plan* p, unsigned chunk, unsigned nchunks)
+{
+  /* 4 is the measured optimum: wider CTAs shorten the global chain further but pile their stores onto
+   * one SM, narrower ones lengthen the chain */
+  unsigned w = p->forced_warps ? p->forced_warps : 4u;
+  if (w > (unsigned)kSmemSamples / chunk) w = (unsigned)kSmemSamples / chunk;
+  if (w > (unsigned)kScanWarps) w = kScanWarps;
+  if (w > nchunks) w = nchunks;
+  if (w < 1) w = 1;
+  return w;
+}
+
+/* production path: the single-pass chained scan/emit kernel (deltas and history are its prologue) */
+template <typename T, typename F>
+bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride, F* part = nullptr,
+                      const cx<F>* weights = nullptr)
+{
+  const unsigned m = (unsigned)p->m;
+  const unsigned ch = (unsigned)p->channels;
+  const int geo = choose_geo(p, n);
+  const unsigned chunk = choose_chunk(p, n, geo);
+  const Schedule sched = make_schedule(p->cursor, n, m, chunk);
+  const unsigned groups = groups_for(p, geo);
+  const size_t wc = (geo == GEO_NARROW) ? (size_t)Geo<F, GEO_NARROW>::WC : (size_t)Geo<F, GEO_WIDE>::WC;
+  const unsigned warps = scan_warps_for(p, chunk, sched.nchunks);
+  const unsigned nblocks = (sched.nchunks + warps - 1) / warps;
+  const size_t items = (size_t)ch * nblocks * groups;
+  if (items >= (1ull << 31))
+  {
+    plan_fail(p, SDFT_B200_ERR_ARG, "analysis: call too large for one launch", __FILE__, __LINE__);
+    return false;
+  }
+
+  if (!reserve(p, p->prefix, items * wc * sizeof(cx<F>))) return false;
+  if (!reserve(p, p->chain_totals, items * wc * sizeof(cx<F>))) return false;
+  const size_t flags_before = p->flags.bytes;
+  if (!reserve(p, p->flags, items * sizeof(unsigned))) return false;
+  if (p->flags.bytes != flags_before || p->epoch >= 0x7ffffff0u)
+  {
+    CU_TRY(p, cudaMemsetAsync(p->flags.ptr, 0, p->flags.bytes, p->stream));
+    p->epoch = 0;
+  }
+  p->epoch++;
+
+  ChainArgs<F> a;
+  a.sched = sched;
+  a.samples = x;
+  a.sample_stride = x_stride;
+  a.hist_old = p->history[p->hist_sel];
+  a.hist_new = p->history[p->hist_sel ^ 1];
+  a.td_double = (type_id<T>::value == kF64) ? 1 : 0;
+  a.scale = (F)p->prescale;
+  a.tw_ext = (const cx<F>*)p->tw_ext;
+  a.f0 = (const cx<F>*)p->f0;
+  a.acc_in = (const cx<F>*)p->acc_state[p->acc_sel];
+  a.acc_out = (cx<F>*)p->acc_state[p->acc_sel ^ 1];
+  a.prefix = (cx<F>*)p->prefix.ptr;
+  a.totals = (cx<F>*)p->chain_totals.ptr;
+  a.flags = (unsigned*)p->flags.ptr;
+  a.control = p->control;
+  a.epoch = p->epoch;
+  a.total_blocks = (unsigned)items;
+  a.nblocks = nblocks;
+  a.channels = ch;
+  a.m = m;
+  a.cells = (unsigned)p->cells;
+  a.out = out;
+  a.out_channel_stride = out_stride;
+  a.tws = weights ? weights : (const cx<F>*)p->tws;
+  a.part = part;
+  a.groups = groups;
+  a.stage_rows = (geo == GEO_NARROW) ? scan_stage_rows<F, GEO_NARROW>(warps, chunk) : scan_stage_rows<F, GEO_WIDE>(warps, chunk);
+  a.win = make_window_const<F>(p->m, p->window);   // sdft.h:422, :371
+  a.trace = nullptr;
+#if defined(SDFT_B200_TRACE)
+  if (reserve(p, p->trace, items * 8 * sizeof(unsigned long long)))
+  {
+    a.trace = (unsigned long long*)p->trace.ptr;
+    p->trace_items = items;
+  }
+#endif
+  if (part)
+  {
+    prof_mark(p, 0);
+    if (p->latency == 1 && !weights) launch_chain<F, EMIT_SYNTH_UNIT>(p, a, false, warps, geo);   // exact compare, sdft.h:639
+    else launch_chain<F, EMIT_SYNTH>(p, a, false, warps, geo);
+    prof_mark(p, 0);
+  }
+  else if (out)
+  {
+    const bool vec = can_vectorize<F>(m, out, out_stride);
+    prof_mark(p, 0);
+    launch_chain<F, EMIT_ROWS>(p, a, vec, warps, geo);
+    prof_mark(p, 0);
+  }
+  else
+  {
+    launch_chain<F, EMIT_NONE>(p, a, false, warps, geo);
+  }
+  CU_TRY(p, cudaGetLastError());
+  p->hist_sel ^= 1;
+  p->cursor = (size_t)((p->cursor + n) % (2 * (size_t)m));
+  p->acc_sel ^= 1;
+  return true;
+}
+
+/* analysis over n samples per channel, everything on the device.
+ * x: (channels, x_stride) samples; out: (channels, out_stride) complex rows or nullptr (state only). */
+template <typename T, typename F>
+bool analysis_device(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride)
+{
+  if (n == 0) return true;
+  return analysis_chained<T, F>(p, n, x, x_stride, out, out_stride);
+}
+
+template <typename T, typename F>
+bool synthesis_device(Plan* p, size_t n, const cx<F>* dfts, size_t dft_stride, T* y, size_t y_stride)
+{
+  if (n == 0) return true;
+  const unsigned ch = (unsigned)p->channels;
+  size_t blocks = (n + kSynthWarps - 1) / kSynthWarps;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const dim3 grid((unsigned)blocks, ch);
+  prof_mark(p, 1);
+  if (p->latency == 1)
+    synth_kernel<T, F, true><<<grid, kSynthWarps * 32, 0, p->stream>>>(dfts, dft_stride, (const cx<F>*)p->tws, y,
+                                                                       y_stride, n, (unsigned)p->m);
+  else
+    synth_kernel<T, F, false><<<grid, kSynthWarps * 32, 0, p->stream>>>(dfts, dft_stride, (const cx<F>*)p->tws, y,
+                                                                        y_stride, n, (unsigned)p->m);
+  prof_mark(p, 1);
+  p->launches++;
+  CU_TRY(p, cudaGetLastError());
+  return true;
+}
+
+}  // namespace
