@@ -463,3 +463,13 @@ def test_config1_testwav(SDFT, golden_dir):
     e = y[delay:].astype(np.float64) - xd
     snr = 10 * np.log10(np.mean(xd ** 2) / np.mean(e ** 2))
     assert abs(snr - float(g["c1_snr_db"])) < 0.01
+    # the same signal in ONE call (5.8 GB of rows, device resident): golden rows, samples and SNR again
+    import torch
+    whole = SDFT(m, "hann", 1, td="f32", fd="f64")
+    rows = whole.sdft(torch.from_numpy(x[:n]).cuda())
+    for k, t in enumerate(want_t):
+        assert rel_err(rows[int(t)].cpu().numpy(), g["c1_rows"][k]) <= 1e-9
+    y1 = whole.isdft(rows).cpu().numpy()
+    assert np.abs(y1 - y).max() <= 2e-6
+    e1 = y1[delay:].astype(np.float64) - xd
+    assert abs(10 * np.log10(np.mean(xd ** 2) / np.mean(e1 ** 2)) - float(g["c1_snr_db"])) < 0.01
