@@ -159,6 +159,13 @@ SDFT_B200_API int sdft_b200_get_twiddles(sdft_b200_plan_t* plan, void* analysis,
 SDFT_B200_API int sdft_b200_get_state(sdft_b200_plan_t* plan, size_t channel, size_t* cursor, void* history,
                                       void* accumulators, void* phase);
 
+/* Import of plan state, the counterpart of sdft_b200_get_state: cursor (0 .. 2*dftsize-1), history
+ * (2*dftsize samples, oldest first) and accumulators (dftsize complex values) from HOST buffers; a NULL
+ * pointer leaves that part unchanged.  This is what exact time sharding uses: a shard
+ * starts from the 2m samples before it and from the sum of the preceding shards' accumulator increments. */
+SDFT_B200_API int sdft_b200_set_state(sdft_b200_plan_t* plan, size_t channel, size_t cursor, const void* history,
+                                      const void* accumulators);
+
 /* Page-locked host memory so that host-pointer calls can DMA straight into the caller's buffer. */
 SDFT_B200_API void* sdft_b200_host_alloc(size_t bytes);
 SDFT_B200_API void sdft_b200_host_free(void* ptr);

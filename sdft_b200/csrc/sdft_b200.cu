@@ -251,6 +251,55 @@ extern "C" int sdft_b200_get_state(sdft_b200_plan_t* p, size_t channel, size_t* 
   return p->status;
 }
 
+/* import: the counterpart of sdft_b200_get_state (HOST buffers; NULL = leave that part as it is) */
+extern "C" int sdft_b200_set_state(sdft_b200_plan_t* p, size_t channel, size_t cursor, const void* history,
+                                   const void* accumulators)
+{
+  if (!p || channel >= p->channels || cursor >= 2 * p->m) return SDFT_B200_ERR_ARG;
+  cudaSetDevice(p->device);
+  const size_t cbytes = (p->fd == kF32) ? sizeof(cx<float>) : sizeof(cx<double>);
+  const size_t tbytes = (p->td == kF32) ? sizeof(float) : sizeof(double);
+  cudaError_t e = cudaStreamSynchronize(p->stream);
+  p->cursor = cursor;          // one cursor per plan: channels of a batch plan advance together
+  if (e == cudaSuccess && history)
+    e = cudaMemcpy((char*)p->history[p->hist_sel] + channel * 2 * p->m * tbytes, history, 2 * p->m * tbytes,
+                   cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && accumulators)
+  {
+    /* extended cell layout: bins at cells 2..m+1, mirror cells as conjugates of their source bins
+     * (make_mirrors); fast double mode keeps the accumulators multiplied by the folded window factor */
+    std::vector<double> cells(2 * p->cells, 0.0);
+    auto bin = [&](size_t k, int part) -> double
+    {
+      return (p->fd == kF32) ? (double)((const float*)accumulators)[2 * k + part] : ((const double*)accumulators)[2 * k + part];
+    };
+    for (size_t k = 0; k < p->m; ++k)
+    {
+      cells[2 * (k + 2)] = bin(k, 0) * p->prescale;
+      cells[2 * (k + 2) + 1] = bin(k, 1) * p->prescale;
+    }
+    for (int q = 0; q < 4; ++q)
+    {
+      const int c = p->mirrors.cell[q], src = p->mirrors.src[q];
+      if (src < 0) continue;
+      cells[2 * c] = bin((size_t)src, 0) * p->prescale;
+      cells[2 * c + 1] = bin((size_t)src, 1) * p->prescale * (p->mirrors.conj[q] ? -1.0 : 1.0);
+    }
+    char* dst = (char*)p->acc_state[p->acc_sel] + channel * p->cells * cbytes;
+    if (p->fd == kF32)
+    {
+      std::vector<float> narrow(cells.begin(), cells.end());
+      e = cudaMemcpy(dst, narrow.data(), p->cells * cbytes, cudaMemcpyHostToDevice);
+    }
+    else
+    {
+      e = cudaMemcpy(dst, cells.data(), p->cells * cbytes, cudaMemcpyHostToDevice);
+    }
+  }
+  if (e != cudaSuccess) plan_fail(p, (int)e, "sdft_b200_set_state", __FILE__, __LINE__);
+  return p->status;
+}
+
 extern "C" void* sdft_b200_host_alloc(size_t bytes)
 {
   void* ptr = nullptr;

@@ -236,5 +236,20 @@ class SDFT:
         self._check()
         return int(cur.value), hist, acc, ph
 
+    def set_state(self, cursor, history=None, accumulators=None, channel=0):
+        """Import plan state (the counterpart of ``state()``): cursor, the last 2*size samples (oldest first)
+        and/or the per-bin accumulators; used to start a time shard exactly where a continuous run would be."""
+        hp = ap = None
+        if history is not None:
+            h = np.ascontiguousarray(history, dtype=_NP_TD[self.td])
+            assert h.shape == (2 * self.size,)
+            hp = h.ctypes.data_as(ctypes.c_void_p)
+        if accumulators is not None:
+            a = np.ascontiguousarray(accumulators, dtype=_NP_FD[self.fd])
+            assert a.shape == (self.size,)
+            ap = a.ctypes.data_as(ctypes.c_void_p)
+        self._lib.sdft_b200_set_state(self._h, channel, int(cursor), hp, ap)
+        self._check()
+
     def set_chunk(self, chunk):
         self._lib.sdft_b200_set_chunk(self._h, int(chunk))

@@ -10,8 +10,16 @@ Two shardings make sense for this path:
   shard starts at cursor 0, exactly where the reference's periodic phase restart falls
   (c/src/sdft/sdft.h:566-576).  The only collective is the optional all-gather of synthesized samples.
 
-Nothing here computes: the planners are pure integer arithmetic and ``gather_samples`` is a thin
-wrapper over ``torch.distributed.all_gather`` (NCCL on GPUs, gloo in the CPU tests).
+  The halo re-seed reproduces the continuous run up to the reference's own delta-rounding random walk
+  (float time domain: ~5e-8 after 2^21 samples) -- fine for float frequency-domain data.
+  The EXACT variant for double frequency-domain data exchanges one row of m complex numbers per rank:
+  every shard first sums its own accumulator increments (``shard_increment``: a state-only pass), the
+  increments are all-gathered (``gather_increments``) and each shard starts from the in-order sum of its
+  predecessors' increments (``start_exact``).
+
+Nothing here computes: the planners are pure integer arithmetic, the state helpers only call the plan's
+``advance`` / ``state`` / ``set_state``, and the gathers are thin wrappers over
+``torch.distributed.all_gather`` (NCCL on GPUs, gloo in the CPU tests).
 """
 from dataclasses import dataclass
 
@@ -70,3 +78,50 @@ def gather_samples(local, shards, group=None):
     parts = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(parts, padded, group=group)
     return torch.cat([p[:s.size] for p, s in zip(parts, shards)])
+
+
+def _halo_history(plan, halo):
+    """The 2m samples in front of a shard as plan history (zero history before the signal's start)."""
+    import numpy as np
+    period = 2 * plan.size
+    h = np.zeros(period, dtype=np.float32 if plan.td == "f32" else np.float64)
+    halo = np.asarray(halo)
+    if halo.size:
+        h[period - halo.size:] = halo[-period:]
+    return h
+
+
+def shard_increment(plan, halo, shard):
+    """Pass 1 of exact time sharding: what this shard adds to every bin's accumulator (m complex values).
+    The plan is left in an undefined state; call ``start_exact`` before analysing the shard."""
+    import numpy as np
+    plan.reset()
+    plan.set_state(0, history=_halo_history(plan, halo),
+                   accumulators=np.zeros(plan.size, np.complex64 if plan.fd == "f32" else np.complex128))
+    plan.advance(shard)
+    return plan.state()[2]
+
+
+def gather_increments(increment, group=None):
+    """All-gathers the per-shard accumulator increments; returns a (world, m) complex array on every rank."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    local = torch.view_as_real(torch.from_numpy(np.ascontiguousarray(increment)))
+    if dist.get_backend(group) == "nccl":
+        local = local.cuda()
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local.contiguous(), group=group)
+    return np.stack([torch.view_as_complex(p.cpu().contiguous()).numpy() for p in parts])
+
+
+def start_exact(plan, halo, increments, rank):
+    """Pass 2: puts the plan exactly where a continuous run would be at the start of shard `rank`:
+    history = the 2m samples before it, accumulators = the preceding shards' increments added in order."""
+    import numpy as np
+    acc = np.zeros(plan.size, np.complex64 if plan.fd == "f32" else np.complex128)
+    for g in range(rank):
+        acc = acc + increments[g].astype(acc.dtype)
+    plan.reset()
+    plan.set_state(0, history=_halo_history(plan, halo), accumulators=acc)

@@ -172,6 +172,39 @@ def test_config3_full_size_shard_independence(torch_cuda):
     print("config 3: SNR %.2f dB (1 shard) / %.2f dB (8 shards)" % (s1, s8))
 
 
+def test_exact_time_sharding_for_double_fd(torch_cuda):
+    """Time shards of a DOUBLE frequency-domain plan with a float time domain: the plain halo re-seed
+    misses the reference's delta-rounding random walk, the exact variant (one row of m
+    accumulator increments exchanged per shard) reproduces the continuous reference run to 1e-9."""
+    from oracle import Oracle
+    from sdft_b200 import SDFT
+    from sdft_b200.shard import shard_increment, start_exact
+    n, m, world = 1 << 18, 512, 4
+    x = workloads.white_noise(n, seed=77)
+    shards = time_shards(n, world, m)
+    walk = Oracle("f32", "f64", m, "hann", 1.0)
+    want, pos = {}, 0
+    for s in shards:
+        walk.advance(x[pos:s.begin])
+        pos = s.begin
+        want[s.rank] = walk.clone().sdft(x[s.begin:s.begin + 64])
+    scale = max(np.abs(w).max() for w in want.values())
+    plans = [SDFT(m, "hann", 1, td="f32", fd="f64") for _ in shards]
+    increments = np.stack([shard_increment(p, x[s.halo_begin:s.begin], x[s.begin:s.end]) for p, s in zip(plans, shards)])
+    worst_exact = worst_halo = 0.0
+    for p, s in zip(plans, shards):
+        start_exact(p, x[s.halo_begin:s.begin], increments, s.rank)
+        got = p.sdft(x[s.begin:s.begin + 64])
+        worst_exact = max(worst_exact, np.abs(got - want[s.rank]).max() / scale)
+        h = SDFT(m, "hann", 1, td="f32", fd="f64")
+        if s.halo:
+            h.advance(x[s.halo_begin:s.begin])
+        worst_halo = max(worst_halo, np.abs(h.sdft(x[s.begin:s.begin + 64]) - want[s.rank]).max() / scale)
+    assert worst_exact <= 1e-9, worst_exact
+    assert worst_halo <= 1e-6          # the plain re-seed: good to the float-delta walk only
+    print("time shards, f32 TD / f64 FD: exact %.3g, halo re-seed %.3g of full scale" % (worst_exact, worst_halo))
+
+
 # --------------------------------------------------------------------------------------------------
 # config 4: independent channels, m = 1024, double FD; one GPU's share (64 of 512 channels x 2^20)
 # --------------------------------------------------------------------------------------------------

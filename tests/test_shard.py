@@ -82,3 +82,30 @@ def test_time_sharded_roundtrip_with_gloo(tmp_path):
     half = time_shards(n, world, m)[0].end
     assert np.array_equal(got[:half], want[:half])
     assert np.abs(got[half:] - want[half:]).max() <= 1e-4 * np.abs(want).max()
+
+
+def _inc_worker(rank, world, port, out_path):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from sdft_b200.shard import gather_increments
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(rank)
+    mine = (rng.uniform(-1, 1, 19) + 1j * rng.uniform(-1, 1, 19)).astype(np.complex128)
+    got = gather_increments(mine)
+    if rank == 1:
+        np.save(out_path, got)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_increments_with_gloo(tmp_path):
+    """The one exchange step of exact time sharding: every rank ends up with all ranks' accumulator increments."""
+    out = str(tmp_path / "inc.npy")
+    mp.spawn(_inc_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    for r in range(2):
+        rng = np.random.default_rng(r)
+        want = (rng.uniform(-1, 1, 19) + 1j * rng.uniform(-1, 1, 19)).astype(np.complex128)
+        assert np.array_equal(got[r], want)
