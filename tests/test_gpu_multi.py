@@ -56,8 +56,20 @@ def _worker(rank, world, port, out_path):
     yc = batch.roundtrip(torch.from_numpy(xc).cuda())
     parts = [torch.empty((hi - lo, nc), dtype=torch.float32, device="cuda") for lo, hi in channel_shards(channels, world)]
     dist.all_gather(parts, yc.reshape(b - a, nc))          # equal shard sizes here (6 channels, world 2)
+    # ---- exact time shards of a double frequency-domain plan: one all-gather of accumulator increments ----
+    from sdft_b200.shard import gather_increments, shard_increment, start_exact
+    ne, me = 1 << 17, 512
+    xe = workloads.white_noise(ne, seed=78)
+    se = time_shards(ne, world, me)[rank]
+    pe = SDFT(me, "hann", 1, td="f32", fd="f64")
+    inc = gather_increments(shard_increment(pe, xe[se.halo_begin:se.begin], xe[se.begin:se.end]))
+    start_exact(pe, xe[se.halo_begin:se.begin], inc, rank)
+    rows_e = torch.from_numpy(pe.sdft(xe[se.begin:se.begin + 32])).cuda()
+    rows_all = [torch.empty_like(rows_e) for _ in range(world)]
+    dist.all_gather(rows_all, rows_e)
     if rank == 0:
-        np.savez(out_path, y_time=y_time.cpu().numpy(), y_chan=torch.cat(parts).cpu().numpy())
+        np.savez(out_path, y_time=y_time.cpu().numpy(), y_chan=torch.cat(parts).cpu().numpy(),
+                 rows_exact=torch.stack(rows_all).cpu().numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -80,6 +92,16 @@ def test_two_gpu_time_and_channel_shards(tmp_path):
     assert np.abs(got["y_time"].astype(np.float64) - want).max() <= 1e-3 * np.abs(want).max()
     delay = int((m - 1) * 0.5)
     assert abs(workloads.snr_db(x, got["y_time"], delay) - workloads.snr_db(x, want, delay)) < 0.01
+
+    ne, me = 1 << 17, 512
+    xe = workloads.white_noise(ne, seed=78)
+    walk, pos = Oracle("f32", "f64", me, "hann", 1.0), 0
+    from sdft_b200.shard import time_shards
+    for s in time_shards(ne, 2, me):
+        walk.advance(xe[pos:s.begin])
+        pos = s.begin
+        want_rows = walk.clone().sdft(xe[s.begin:s.begin + 32])
+        assert np.abs(got["rows_exact"][s.rank] - want_rows).max() <= 1e-9 * np.abs(want_rows).max(), s.rank
 
     for c in range(6):
         xc = workloads.channel_noise(c, 20000)
