@@ -318,5 +318,5 @@ extern "C" void sdft_b200_host_free(void* ptr)
 
 extern "C" const char* sdft_b200_version(void)
 {
-  return "sdft_b200 0.1 (sm_100a; analysis: chunked two-pass scan; synthesis: warp reduction)";
+  return "sdft_b200 0.2 (sm_100a; analysis: single-pass chained scan + emit; synthesis: warp reduction; fused round trip)";
 }
