@@ -143,6 +143,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU reference leg (the only place that touches oracle/)
 # ------------------------------------------------------------------------------------------------
+SYNTH = {}   # synthesis samples/s of the last cpu_reference_run: {"all": ..., "single": ...}
+
+
 def cpu_reference_run(samples_per_window, threads, steps, warmup):
     """One channel per host thread through the reference's sdft_sdft_n (all four windows per step).
     Returns (bin-updates/s aggregate, seconds per step, kind, single-thread bin-updates/s)."""
@@ -180,6 +183,28 @@ def cpu_reference_run(samples_per_window, threads, steps, warmup):
     per_step = total / steps
     agg = threads * 4 * samples_per_window * M / per_step
     single = 4 * samples_per_window * M / step(1)
+
+    # synthesis (sdft_isdft_n) over the rows just produced: all threads, then one
+    ys = [np.zeros(samples_per_window, np.float32) for _ in range(threads)]
+
+    def synth(t):
+        p = plans[t][1]
+        fn = p._fn("ref_isdft_n" if kind == "reference" else "isdft_n", None,
+                   [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p])
+        fn(p.h, samples_per_window, outs[t].ctypes.data_as(ctypes.c_void_p), ys[t].ctypes.data_as(ctypes.c_void_p))
+
+    def synth_step(nthreads):
+        ts = [threading.Thread(target=synth, args=(t,)) for t in range(nthreads)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
+
+    synth_step(threads)
+    SYNTH["all"] = threads * samples_per_window / min(synth_step(threads), synth_step(threads))
+    SYNTH["single"] = samples_per_window / min(synth_step(1), synth_step(1))
     return agg, per_step, kind, single
 
 
@@ -231,7 +256,8 @@ def run_reference_arm(args, rank, world):
         "config": {"workload": "configs[1]: white noise, m=4096, f32 TD / f64 FD, four windows; reference C "
                                "sdft_sdft_n on host cores, bounded sample", "m": M, "sample": sample},
         "cpu_baseline": {"value": agg, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
-                         "single_thread": single},
+                         "single_thread": single, "synthesis_samples_per_s": SYNTH.get("all"),
+                         "synthesis_single_thread_samples_per_s": SYNTH.get("single")},
         "e2e": {"value": agg, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "hop_pattern": {"value": cpu_hop_pattern(2048, threads), "unit": UNIT,
                                 "sample": "sdft_sdft_n + sdft_isdft_n per hop (test/test.c:79-80), hann, 2048-sample hops, "
@@ -566,6 +592,7 @@ def run_b200_arm(args, rank, local_rank, world):
         spw = 4096
         agg, per_step, kind, single = cpu_reference_run(spw, threads, 2, 1)
         cpu = {"value": agg, "unit": UNIT, "cores": threads, "kind": kind, "single_thread": single,
+               "synthesis_samples_per_s": SYNTH.get("all"), "synthesis_single_thread_samples_per_s": SYNTH.get("single"),
                "sample": "%d host threads x 4 windows x %d samples, one channel per thread, m=%d" % (threads, spw, m)}
 
     if rank == 0:
