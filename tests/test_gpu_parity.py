@@ -181,6 +181,27 @@ def test_randomized_plans_and_call_sequences(SDFT, seed, monkeypatch):
         assert cg == co and np.array_equal(_bits(hg), _bits(ho)) and rel_err(ag, ao) <= TOL[fd]
 
 
+@pytest.mark.parametrize("m,fd", [(16384, "f64"), (10007, "f64"), (10007, "f32"), (8192, "f32")])
+def test_large_and_odd_dft_sizes(SDFT, m, fd):
+    """Big plans (phase table of hundreds of MiB) and an odd prime size (rows not 32-byte aligned: the
+    bin-by-bin store path), over calls that cross the 2m period."""
+    from oracle import Oracle
+    rng = np.random.default_rng(m)
+    g = SDFT(m, "blackman", 0.5, td="f32", fd=fd)
+    o = Oracle("f32", fd, m, "blackman", 0.5)
+    for n in (700, 1500, 1):
+        x = rng.uniform(-1, 1, n).astype(np.float32)
+        want, got = o.sdft(x), g.sdft(x)
+        assert rel_err(got, want) <= TOL[fd], (m, n, rel_err(got, want))
+        assert np.abs(g.isdft(got).astype(np.float64) - o.isdft(want)).max() <= (2e-6 if fd == "f64" else 2e-4)
+    x2 = rng.uniform(-1, 1, 2 * m).astype(np.float32)            # across the period boundary, state only
+    g.advance(x2)
+    o.advance(x2)
+    x3 = rng.uniform(-1, 1, 40).astype(np.float32)
+    assert rel_err(g.sdft(x3), o.sdft(x3)) <= TOL[fd]
+    assert g.state()[0] == o.state()[0]
+
+
 def test_reset_and_getters(SDFT):
     from oracle import Oracle
     g = SDFT(16, "hamming", 0.5, td="f32", fd="f64")
