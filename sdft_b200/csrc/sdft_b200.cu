@@ -14,6 +14,7 @@
 #include "../../include/sdft_b200.h"
 #include "sdft_kernels.cuh"
 #include "sdft_host_copy.hpp"
+#include "sdft_tables.hpp"
 
 #include <vector>
 #include <cmath>
