@@ -147,11 +147,12 @@ void launch_chain(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps, int 
 }
 
 /* warps (= consecutive chunks) per scan/emit CTA */
-unsigned scan_warps_for(const Plan* p, unsigned chunk, unsigned nchunks)
+unsigned scan_warps_for(const Plan* p, unsigned chunk, unsigned nchunks, int geo)
 {
   /* 4 is the measured optimum: wider CTAs shorten the global chain further but pile their stores onto
-   * one SM, narrower ones lengthen the chain */
-  unsigned w = p->forced_warps ? p->forced_warps : 4u;
+   * one SM, narrower ones lengthen the chain; long chains of narrow warps gain a few per cent from 8
+   * (tools/narrow_sweep.py) */
+  unsigned w = p->forced_warps ? p->forced_warps : ((geo == GEO_NARROW && nchunks >= 128u) ? 8u : 4u);
   if (w > (unsigned)kSmemSamples / chunk) w = (unsigned)kSmemSamples / chunk;
   if (w > (unsigned)kScanWarps) w = kScanWarps;
   if (w > nchunks) w = nchunks;
@@ -171,7 +172,7 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   const Schedule sched = make_schedule(p->cursor, n, m, chunk);
   const unsigned groups = groups_for(p, geo);
   const size_t wc = (geo == GEO_NARROW) ? (size_t)Geo<F, GEO_NARROW>::WC : (size_t)Geo<F, GEO_WIDE>::WC;
-  const unsigned warps = scan_warps_for(p, chunk, sched.nchunks);
+  const unsigned warps = scan_warps_for(p, chunk, sched.nchunks, geo);
   const unsigned nblocks = (sched.nchunks + warps - 1) / warps;
   const size_t items = (size_t)ch * nblocks * groups;
   if (items >= (1ull << 31))
