@@ -304,40 +304,124 @@ bool do_isdft_nd(Plan* p, size_t n, const cx<F>** rows_in, T* samples)
 /* analysis -> synthesis in ONE kernel: the rows never exist in memory.  Every warp weighs and reduces
  * its bins per time step (SynthLane), per-group partial sums go to a scratch buffer and a small second
  * kernel adds the groups in order.  Long calls are cut into pieces that bound the scratch. */
+/* Synthesis weights with the window folded in (the adjoint of sdft_etc_convolve, sdft.h:350-402, mirror cells
+ * of sdft.h:589-595 folded onto their source bins): for v[k] the per-bin factor of sdft_isdft (sdft.h:639-652),
+ *     sum_k Re(v[k] * sum_j T[j] aux[k + j])  =  sum_b (A[b] Re(aux[b]) + B[b] Im(aux[b])).
+ * `ab` receives (A, B) per bin; returns true when every B is zero (latency 1 without gains). */
+template <typename F>
+bool make_synth_weights(const Plan* p, const std::vector<cx<double>>& v, std::vector<F>& ab)
+{
+  const long m = (long)p->m;
+  const WindowConst<F> wc = make_window_const<F>(p->m, p->window);
+  const double w = (double)wc.w;
+  double taps[5] = { 0, 0, w, 0, 0 };                       // T[-2 .. +2]
+  if (p->window == 1) { taps[2] = 0.5 * w; taps[1] = taps[3] = -0.25 * w; }
+  if (p->window == 2) { taps[2] = (double)(F)0.54 * w; taps[1] = taps[3] = -(double)(F)0.23 * w; }
+  if (p->window == 3) { taps[2] = (double)(F)0.42 * w; taps[1] = taps[3] = -(double)(F)0.25 * w; taps[0] = taps[4] = (double)(F)0.04 * w; }
+  std::vector<double> A(m, 0.0), B(m, 0.0);
+  for (long k = 0; k < m; ++k)
+  {
+    for (int j = -2; j <= 2; ++j)
+    {
+      const double t = taps[j + 2];
+      if (t == 0.0) continue;
+      long cell = k + 2 + j, bin = cell - 2;
+      bool conj = false;
+      if (cell < 2 || cell >= m + 2)
+      {
+        int q = -1;
+        for (int i = 0; i < 4; ++i)
+          if (p->mirrors.cell[i] == (int)cell) q = i;
+        if (q < 0 || p->mirrors.src[q] < 0) continue;       // a cell that is always zero
+        bin = p->mirrors.src[q];
+        conj = p->mirrors.conj[q] != 0;
+      }
+      /* Re(v a) = vr ar - vi ai ;  Re(v conj(a)) = vr ar + vi ai */
+      A[bin] += t * v[k].r;
+      B[bin] += (conj ? +t : -t) * v[k].i;
+    }
+  }
+  /* double fast mode replays pre-scaled spectra (the window weight is folded into the deltas) */
+  const double unscale = 1.0 / p->prescale;
+  ab.resize(2 * (size_t)m);
+  bool unit = true;
+  for (long b = 0; b < m; ++b)
+  {
+    ab[2 * b] = (F)(A[b] * unscale);
+    ab[2 * b + 1] = (F)(B[b] * unscale);
+    if (ab[2 * b + 1] != (F)0) unit = false;
+  }
+  return unit;
+}
+
+/* the per-bin factor of sdft_isdft: (-1)^k for latency 1 (exact compare, sdft.h:639), tws[k] otherwise,
+ * times an optional spectral gain */
+template <typename F>
+std::vector<cx<double>> synth_factors(const Plan* p, const cx<F>* gains_host)
+{
+  const size_t m = p->m;
+  std::vector<cx<F>> tw, tws;
+  make_tables<F>(m, p->latency, tw, tws);
+  std::vector<cx<double>> v(m);
+  for (size_t k = 0; k < m; ++k)
+  {
+    cx<double> t;
+    t.r = (double)tws[k].r; t.i = (double)tws[k].i;
+    if (p->latency == 1) { t.r = (k & 1) ? -1.0 : 1.0; t.i = 0.0; }
+    if (gains_host)
+    {
+      const double gr = (double)gains_host[k].r, gi = (double)gains_host[k].i;
+      const cx<double> u = t;
+      t.r = gr * u.r - gi * u.i;
+      t.i = gr * u.i + gi * u.r;
+    }
+    v[k] = t;
+  }
+  return v;
+}
+
+/* analysis -> synthesis in ONE kernel: the rows never exist in memory.  Every warp weighs and reduces
+ * its bins per time step (SynthLane), per-group partial sums go to a scratch buffer and a small second
+ * kernel adds the groups in order.  Long calls are cut into pieces that bound the scratch.
+ * `gains`: spectral processing between analysis and synthesis -- every row is multiplied bin by bin with
+ * `gains` before sdft_isdft sees it. */
 template <typename T, typename F>
 bool do_roundtrip(Plan* p, size_t n, const T* in, T* out, const cx<F>* gains = nullptr)
 {
   if (n == 0) return true;
   CU_TRY(p, cudaSetDevice(p->device));
-  const cx<F>* weights = nullptr;
-  if (gains)
+  const size_t m = p->m;
+  const F* syn_ab = nullptr;
+  bool syn_unit = false;
+  if (gains || !p->syn_ab_ready)
   {
-    /* spectral processing between analysis and synthesis: every row is multiplied bin by bin with
-     * `gains` before sdft_isdft sees it, i.e. the synthesis weights become gains[k] * tws[k]
-     * (gains[k] * (-1)^k for latency 1, sdft.h:639-652) */
-    const size_t m = p->m;
-    std::vector<cx<F>> g(m), w(m);
-    if (classify(gains) == kDevice) CU_TRY(p, cudaMemcpy(g.data(), gains, m * sizeof(cx<F>), cudaMemcpyDeviceToHost));
-    else memcpy(g.data(), gains, m * sizeof(cx<F>));
-    std::vector<cx<F>> tw, tws;
-    make_tables<F>(m, p->latency, tw, tws);
-    for (size_t k = 0; k < m; ++k)
+    std::vector<cx<F>> g;
+    if (gains)
     {
-      cx<F> t = tws[k];
-      if (p->latency == 1) { t.r = (k & 1) ? (F)(-1) : (F)(1); t.i = (F)0; }
-      w[k].r = g[k].r * t.r - g[k].i * t.i;
-      w[k].i = g[k].r * t.i + g[k].i * t.r;
+      g.resize(m);
+      if (classify(gains) == kDevice) CU_TRY(p, cudaMemcpy(g.data(), gains, m * sizeof(cx<F>), cudaMemcpyDeviceToHost));
+      else memcpy(g.data(), gains, m * sizeof(cx<F>));
     }
-    if (!reserve(p, p->weights, m * sizeof(cx<F>))) return false;
-    CU_TRY(p, cudaMemcpyAsync(p->weights.ptr, w.data(), m * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
-    CU_TRY(p, cudaStreamSynchronize(p->stream));   // w goes out of scope
-    weights = (const cx<F>*)p->weights.ptr;
+    std::vector<F> ab;
+    const bool unit = make_synth_weights<F>(p, synth_factors<F>(p, gains ? g.data() : nullptr), ab);
+    Buffer& dst = gains ? p->weights : p->syn_ab;
+    if (!reserve(p, dst, 2 * m * sizeof(F))) return false;
+    CU_TRY(p, cudaMemcpyAsync(dst.ptr, ab.data(), 2 * m * sizeof(F), cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(p, cudaStreamSynchronize(p->stream));   // ab goes out of scope
+    if (!gains) { p->syn_ab_ready = true; p->syn_ab_unit = unit; }
+    syn_ab = (const F*)dst.ptr;
+    syn_unit = unit;
+  }
+  else
+  {
+    syn_ab = (const F*)p->syn_ab.ptr;
+    syn_unit = p->syn_ab_unit;
   }
   bool ok = true;
   const T* x = stage_samples<T>(p, n, in, &ok);
   if (!ok) return false;
   const size_t ch = p->channels;
-  const unsigned max_groups = groups_for(p, GEO_NARROW);    // either geometry may be chosen per piece
+  const unsigned max_groups = groups_for(p, GEO_NARROW, true);    // either geometry may be chosen per piece
   const bool out_dev = classify(out) == kDevice;
   T* y = out;
   if (!out_dev)
@@ -351,8 +435,8 @@ bool do_roundtrip(Plan* p, size_t n, const T* in, T* out, const cx<F>* gains = n
   for (size_t t0 = 0; t0 < n; t0 += piece)
   {
     const size_t len = (t0 + piece <= n) ? piece : n - t0;
-    const unsigned groups = groups_for(p, choose_geo(p, len));   // what analysis_chained will use for this piece
-    if (!analysis_chained<T, F>(p, len, x + t0, n, (cx<F>*)nullptr, 0, (F*)p->part.ptr, weights)) return false;
+    const unsigned groups = groups_for(p, choose_geo(p, len), true);   // what analysis_chained will use for this piece
+    if (!analysis_chained<T, F>(p, len, x + t0, n, (cx<F>*)nullptr, 0, (F*)p->part.ptr, syn_ab, syn_unit)) return false;
     size_t blocks = (len + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     synth_finish_kernel<T, F><<<dim3((unsigned)blocks, (unsigned)ch), 256, 0, p->stream>>>(

@@ -141,13 +141,13 @@ struct EmitLane
     store_rows(y, row_stride);
   }
 
-  /* one time step of the modulated replay: windowed spectrum of this lane's cells into y[] */
+  /* one time step of the modulated replay WITHOUT the window: the demodulated spectrum of this lane's
+   * cells (sdft.h:583-585) into x[] */
   template <bool RESTART, bool FUSED>
-  __device__ __forceinline__ void compute(F d, const cx<F>* restart, const WindowConst<F>& win, cx<F>* y)
+  __device__ __forceinline__ void advance(F d, const cx<F>* restart, cx<F>* x)
   {
     typedef Arith<F> A;
     typedef StageOps<F, FUSED> S;
-    cx<F> x[G::CPL];
 #pragma unroll
     for (int b = 0; b < G::CPL; ++b)
     {
@@ -155,6 +155,15 @@ struct EmitLane
       ph[b] = RESTART ? restart[b] : A::rotate(ph[b], tw[b]);
       x[b] = S::demod(acc[b], ph[b]);
     }
+  }
+
+  /* one time step of the modulated replay: windowed spectrum of this lane's cells into y[] */
+  template <bool RESTART, bool FUSED>
+  __device__ __forceinline__ void compute(F d, const cx<F>* restart, const WindowConst<F>& win, cx<F>* y)
+  {
+    typedef StageOps<F, FUSED> S;
+    cx<F> x[G::CPL];
+    advance<RESTART, FUSED>(d, restart, x);
     if (WINDOW == 0)
     {
 #pragma unroll
@@ -258,48 +267,48 @@ struct EmitLane
 };
 
 /* ------------------------------------------------------------------------------------------------
- * Fused synthesis (EMIT_SYNTH): instead of storing the rows, every lane weighs its bins as sdft_isdft
- * does (sdft.h:639-652: (-1)^k Re(dft[k]) for latency 1, Re(dft[k] * tws[k]) otherwise) and the warp
- * reduces eight time steps at once with a transposing butterfly (9 shuffles per 8 steps instead of 5
- * per step): after three exchange rounds every lane holds ONE step's sum over eight lanes, two plain
- * butterfly rounds finish it.  The warp's partial sums over its bins go to part[group][t]; a second
- * tiny kernel adds the groups in order and scales by 2 (sdft.h:654-656).  Fixed order: deterministic.
+ * Fused synthesis (EMIT_SYNTH): instead of storing the rows, every lane weighs its bins and the warp
+ * reduces over the bins.  The window never runs on the device here: sdft_isdft of a windowed row is
+ *     y = 2 sum_k Re(v[k] * sum_j T[j] aux[k + j])          v = (-1)^k or tws[k]   (sdft.h:639-652),
+ * linear in aux, so the taps T are moved onto the weights on the host (the adjoint of sdft_etc_convolve,
+ * mirror cells folded onto their source bins, make_synth_weights):
+ *     y = 2 sum_b (A[b] Re(aux[b]) + B[b] Im(aux[b])).
+ * No halo, no shuffles across bins, 1-2 FMAs per bin instead of the 4-10 of the taps.  The warp reduces
+ * eight time steps at once with a transposing butterfly (9 shuffles per 8 steps instead of 5 per step):
+ * after three exchange rounds every lane holds ONE step's sum over eight lanes, two plain butterfly
+ * rounds finish it.  The warp's partial sums go to part[group][t]; a second tiny kernel adds the groups in
+ * order and scales by 2 (sdft.h:654-656).  Fixed order: deterministic.
  * ---------------------------------------------------------------------------------------------- */
 template <typename F, int CPL, bool UNIT>
 struct SynthLane
 {
-  F wr[CPL], wi[CPL];   // weights of this lane's bins; 0 for halo / out-of-range cells
+  F wa[CPL], wb[CPL];   // weights of Re / Im of this lane's bins (wb all zero when UNIT); 0 beyond bin m-1
+  F wsum;               // sum of wa[]: what a constant added to every cell's real part contributes
   F p[8];
 
-  __device__ __forceinline__ void setup(const cx<F>* __restrict__ tws, int e0, const bool* ok)
+  __device__ __forceinline__ void setup(const F* __restrict__ ab, int e0, const bool* ok)
   {
+    wsum = (F)0;
 #pragma unroll
     for (int b = 0; b < CPL; ++b)
     {
       const int k = e0 + b - 2;
-      if (UNIT)
-      {
-        wr[b] = ok[b] ? ((k & 1) ? (F)(-1) : (F)(1)) : (F)0;
-        wi[b] = (F)0;
-      }
-      else
-      {
-        wr[b] = ok[b] ? tws[k].r : (F)0;
-        wi[b] = ok[b] ? tws[k].i : (F)0;
-      }
+      wa[b] = ok[b] ? ab[2 * k] : (F)0;
+      wb[b] = (ok[b] && !UNIT) ? ab[2 * k + 1] : (F)0;
+      wsum += wa[b];
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) p[i] = (F)0;
   }
 
-  __device__ __forceinline__ F weigh(const cx<F>* y) const
+  __device__ __forceinline__ F weigh(const cx<F>* x) const
   {
     F s = (F)0;
 #pragma unroll
     for (int b = 0; b < CPL; ++b)
     {
-      s = fma(y[b].r, wr[b], s);
-      if (!UNIT) s = fma(-y[b].i, wi[b], s);
+      s = fma(x[b].r, wa[b], s);
+      if (!UNIT) s = fma(x[b].i, wb[b], s);
     }
     return s;
   }

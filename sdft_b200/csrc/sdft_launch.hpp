@@ -22,7 +22,7 @@ void prof_mark(Plan* p, int which)
 }
 
 /* warp-wide groups of bins the plan's m bins are cut into, for either warp geometry */
-unsigned groups_for(const Plan* p, int geo = GEO_WIDE)
+unsigned groups_for(const Plan* p, int geo = GEO_WIDE, bool no_halo = false)
 {
   unsigned wc, halo;
   if (p->fd == kF32)
@@ -35,7 +35,7 @@ unsigned groups_for(const Plan* p, int geo = GEO_WIDE)
     wc = geo == GEO_WIDE ? (unsigned)Geo<double, GEO_WIDE>::WC : (unsigned)Geo<double, GEO_NARROW>::WC;
     halo = (unsigned)Geo<double, GEO_WIDE>::GROUP;
   }
-  if (p->window == 0) halo = 0;
+  if (p->window == 0 || no_halo) halo = 0;    // the fused synthesis folds the window into its weights: no taps, no halo
   const unsigned span = wc - 2 * halo;
   return (unsigned)((p->m + span - 1) / span);
 }
@@ -113,10 +113,11 @@ void launch_chain_geo(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps)
     if (vec) cudaLaunchKernelEx(&cfg, scan_emit_kernel<F, W, true, EMIT, MODE, GEO>, a);               \
     else cudaLaunchKernelEx(&cfg, scan_emit_kernel<F, W, false, EMIT, MODE, GEO>, a);                  \
     break;
+  const int window = (EMIT == EMIT_SYNTH_UNIT || EMIT == EMIT_SYNTH) ? 0 : p->window;   // no taps in the fused synthesis
   if (GEO == GEO_NARROW || p->mode == kDefaultMode)
   {
     /* the narrow geometry exists for the default mode only (choose_geo) */
-    switch (p->window)
+    switch (window)
     {
       SDFT_CHAIN_CASE(0, kDefaultMode)
       SDFT_CHAIN_CASE(1, kDefaultMode)
@@ -127,7 +128,7 @@ void launch_chain_geo(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps)
   else if constexpr (GEO == GEO_WIDE)
   {
     constexpr int kOtherMode = (kDefaultMode == (int)MODE_FAST) ? (int)MODE_MODULATED : (int)MODE_FAST;
-    switch (p->window)
+    switch (window)
     {
       SDFT_CHAIN_CASE(0, kOtherMode)
       SDFT_CHAIN_CASE(1, kOtherMode)
@@ -163,14 +164,14 @@ unsigned scan_warps_for(const Plan* p, unsigned chunk, unsigned nchunks, int geo
 /* production path: the single-pass chained scan/emit kernel (deltas and history are its prologue) */
 template <typename T, typename F>
 bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride, F* part = nullptr,
-                      const cx<F>* weights = nullptr)
+                      const F* syn_ab = nullptr, bool syn_unit = false)
 {
   const unsigned m = (unsigned)p->m;
   const unsigned ch = (unsigned)p->channels;
   const int geo = choose_geo(p, n);
   const unsigned chunk = choose_chunk(p, n, geo);
   const Schedule sched = make_schedule(p->cursor, n, m, chunk);
-  const unsigned groups = groups_for(p, geo);
+  const unsigned groups = groups_for(p, geo, part != nullptr);
   const size_t wc = (geo == GEO_NARROW) ? (size_t)Geo<F, GEO_NARROW>::WC : (size_t)Geo<F, GEO_WIDE>::WC;
   const unsigned warps = scan_warps_for(p, chunk, sched.nchunks, geo);
   const unsigned nblocks = (sched.nchunks + warps - 1) / warps;
@@ -216,7 +217,7 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   a.cells = (unsigned)p->cells;
   a.out = out;
   a.out_channel_stride = out_stride;
-  a.tws = weights ? weights : (const cx<F>*)p->tws;
+  a.syn_ab = syn_ab;
   a.part = part;
   a.groups = groups;
   a.stage_rows = (geo == GEO_NARROW) ? scan_stage_rows<F, GEO_NARROW>(warps, chunk) : scan_stage_rows<F, GEO_WIDE>(warps, chunk);
@@ -232,7 +233,7 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   if (part)
   {
     prof_mark(p, 0);
-    if (p->latency == 1 && !weights) launch_chain<F, EMIT_SYNTH_UNIT>(p, a, false, warps, geo);   // exact compare, sdft.h:639
+    if (syn_unit) launch_chain<F, EMIT_SYNTH_UNIT>(p, a, false, warps, geo);   // all imaginary-part weights are zero
     else launch_chain<F, EMIT_SYNTH>(p, a, false, warps, geo);
     prof_mark(p, 0);
   }

@@ -65,6 +65,8 @@ struct sdft_b200_plan
   void* phase_scratch = nullptr;   // cells complex values, introspection only
 
   Buffer samples, synth_out, tile[2], part, weights;
+  Buffer syn_ab;                 // fused synthesis: per-bin (A, B) weights with the window folded in (make_synth_weights)
+  bool syn_ab_ready = false, syn_ab_unit = false;
   Buffer trace;                  // -DSDFT_B200_TRACE builds: per-CTA phase stamps of the last scan launch
   size_t trace_items = 0;
   void* stage[2] = { nullptr, nullptr };   // pinned host staging for PAGEABLE caller buffers (grow-only)
@@ -299,7 +301,7 @@ void plan_destroy(Plan* p)
   if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
   void* ptrs[] = { p->tw_ext, p->tws, p->f0, p->history[0], p->history[1], p->acc_state[0], p->acc_state[1], p->phase_scratch,
                    p->prefix.ptr, p->chain_totals.ptr, p->flags.ptr, p->control,
-                   p->samples.ptr, p->synth_out.ptr, p->part.ptr, p->weights.ptr, p->trace.ptr, p->tile[0].ptr, p->tile[1].ptr };
+                   p->samples.ptr, p->synth_out.ptr, p->part.ptr, p->weights.ptr, p->syn_ab.ptr, p->trace.ptr, p->tile[0].ptr, p->tile[1].ptr };
   for (void* q : ptrs)
     if (q) cudaFree(q);
   for (int w = 0; w < 2; ++w)

@@ -76,7 +76,7 @@ template <typename F> struct ChainArgs
   unsigned cells;
   cx<F>* out;              // (channels, n, m) or nullptr
   size_t out_channel_stride;
-  const cx<F>* tws;        // (m) synthesis twiddles, EMIT_SYNTH only
+  const F* syn_ab;         // (m, 2) synthesis weights of Re / Im of every bin with the window folded in, EMIT_SYNTH only
   F* part;                 // (channels, groups, n) per-group partial sums of the fused synthesis
   unsigned groups;
   unsigned stage_rows;     // rows of look-back staging in shared memory (scan_stage_rows)
@@ -320,6 +320,27 @@ __device__ __forceinline__ void look_back(const ChainArgs<F>& a, size_t item, si
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b) acc[b] = A::cadd(acc[b], mine[(size_t)u * G::WC + b]);
     r += batch;
+  }
+}
+
+/* one time step of the fused synthesis for one lane: advance the replay, weigh the (un-windowed) spectrum.
+ * SLIDE (double fast mode): acc holds z = aux + delta_next in every cell, so the constant is taken out
+ * again through the sum of the real-part weights (SynthLane::wsum). */
+template <bool RESTART, typename F, bool SLIDE, bool FUSED, typename Lane, typename Syn>
+__device__ __forceinline__ F synth_step_impl(Lane& L, const Syn& syn, const F* sdelta, unsigned i, const cx<F>* restart)
+{
+  if constexpr (SLIDE)
+  {
+    const F d_next = sdelta[i + 1];
+#pragma unroll
+    for (int b = 0; b < Lane::G::CPL; ++b) L.acc[b] = Arith<F>::horner(L.acc[b], L.tw[b], d_next);
+    return fma(-d_next, syn.wsum, syn.weigh(L.acc));
+  }
+  else
+  {
+    cx<F> x[Lane::G::CPL];
+    L.template advance<RESTART, FUSED>(sdelta[i], restart, x);
+    return syn.weigh(x);
   }
 }
 
@@ -646,7 +667,7 @@ SDFT_B200_PRAGMA_UNROLL(SDFT_B200_EMIT_UNROLL)
     /* fused synthesis: the rows never leave the registers (see SynthLane) */
     typedef SynthLane<F, G::CPL, EMIT == EMIT_SYNTH_UNIT> Y;
     Y syn;
-    syn.setup(a.tws, e0, L.ok);
+    syn.setup(a.syn_ab, e0, L.ok);
     F* pdst = a.part + ((size_t)ch * a.groups + group) * a.sched.n + cs.t0;
     const unsigned slot = Y::step_of(lane);
     const bool writer = (lane & 3u) == 0u;
@@ -678,29 +699,18 @@ SDFT_B200_PRAGMA_UNROLL(SDFT_B200_EMIT_UNROLL)
     for (; i + 8 <= body; i += 8)
     {
 #pragma unroll
-      for (unsigned u = 0; u < 8; ++u)
-      {
-        cx<F> y[G::CPL];
-        if constexpr (SLIDE) L.fast_compute(sdelta[i + u + 1], a.win, y);
-        else L.template compute<false, FUSED>(sdelta[i + u], restart, a.win, y);
-        syn.p[u] = syn.weigh(y);
-      }
+      for (unsigned u = 0; u < 8; ++u) syn.p[u] = synth_step_impl<false, F, SLIDE, FUSED>(L, syn, sdelta, i + u, restart);
       const F total = syn.reduce8(lane);
       if (writer) pdst[i + slot] = total;
     }
     for (; i < body; ++i)
     {
-      cx<F> y[G::CPL];
-      if constexpr (SLIDE) L.fast_compute(sdelta[i + 1], a.win, y);
-      else L.template compute<false, FUSED>(sdelta[i], restart, a.win, y);
-      const F total = Y::warp_sum(syn.weigh(y));
+      const F total = Y::warp_sum(synth_step_impl<false, F, SLIDE, FUSED>(L, syn, sdelta, i, restart));
       if (lane == 0) pdst[i] = total;
     }
     if (!SLIDE && cs.wraps)
     {
-      cx<F> y[G::CPL];
-      L.template compute<true, FUSED>(sdelta[body], restart, a.win, y);
-      const F total = Y::warp_sum(syn.weigh(y));
+      const F total = Y::warp_sum(synth_step_impl<true, F, SLIDE, FUSED>(L, syn, sdelta, body, restart));
       if (lane == 0) pdst[body] = total;
     }
   }
