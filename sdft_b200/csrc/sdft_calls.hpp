@@ -28,13 +28,25 @@ const T* stage_samples(Plan* p, size_t n, const T* samples, bool* ok)
   if (classify(samples) == kDevice) return samples;
   const size_t bytes = p->channels * n * sizeof(T);
   if (!reserve(p, p->samples, bytes)) { *ok = false; return nullptr; }
-  if (cudaMemcpyAsync(p->samples.ptr, samples, bytes, cudaMemcpyHostToDevice, p->stream) != cudaSuccess)
+  if (cudaMemcpyAsync(p->samples.ptr, samples, bytes, cudaMemcpyHostToDevice, p->stream) != cudaSuccess ||
+      cudaEventRecord(p->samples_in, p->stream) != cudaSuccess)
   {
     plan_fail(p, (int)cudaGetLastError(), "H2D samples", __FILE__, __LINE__);
     *ok = false;
     return nullptr;
   }
+  p->samples_in_flight = true;     // a page-locked source is read asynchronously: see release_samples
   return (const T*)p->samples.ptr;
+}
+
+/* a call that returns while its kernels are still queued (device destination) must at least have finished
+ * reading the caller's HOST samples: the caller may overwrite them as soon as the call returns */
+bool release_samples(Plan* p)
+{
+  if (!p->samples_in_flight) return true;
+  p->samples_in_flight = false;
+  CU_TRY(p, cudaEventSynchronize(p->samples_in));
+  return true;
 }
 
 template <typename T, typename F>
@@ -49,7 +61,7 @@ bool do_sdft(Plan* p, size_t n, const T* samples, cx<F>* dfts)
 
   if (classify(dfts) == kDevice)
   {
-    return analysis_device<T, F>(p, n, x, n, dfts, n * m);
+    return analysis_device<T, F>(p, n, x, n, dfts, n * m) && release_samples(p);
   }
 
   /* host destination: compute row tiles on the device and stream them out, overlapping the
@@ -124,6 +136,7 @@ bool do_sdft(Plan* p, size_t n, const T* samples, cx<F>* dfts)
   }
   CU_TRY(p, cudaStreamSynchronize(p->copy_stream));
   CU_TRY(p, cudaStreamSynchronize(p->stream));
+  p->samples_in_flight = false;
   return true;
 }
 
@@ -448,8 +461,10 @@ bool do_roundtrip(Plan* p, size_t n, const T* in, T* out, const cx<F>* gains = n
   {
     CU_TRY(p, cudaMemcpyAsync(out, y, ch * n * sizeof(T), cudaMemcpyDeviceToHost, p->stream));
     CU_TRY(p, cudaStreamSynchronize(p->stream));
+    p->samples_in_flight = false;
+    return true;
   }
-  return true;
+  return release_samples(p);
 }
 
 /* SDFT.convolve of the reference's Python class (python/src/sdft/sdft.py:146-203): window(rows) / m */

@@ -38,6 +38,8 @@ struct sdft_b200_plan
   cudaStream_t own_stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaEvent_t samples_in = nullptr;       // recorded after the host-to-device copy of a call's samples
+  bool samples_in_flight = false;
   cudaEvent_t tile_ready[2] = { nullptr, nullptr };
   cudaEvent_t tile_free[2] = { nullptr, nullptr };
 
@@ -313,6 +315,7 @@ void plan_destroy(Plan* p)
     if (p->tile_ready[i]) cudaEventDestroy(p->tile_ready[i]);
     if (p->tile_free[i]) cudaEventDestroy(p->tile_free[i]);
   }
+  if (p->samples_in) cudaEventDestroy(p->samples_in);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
   if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
   cudaGetLastError();
@@ -383,6 +386,7 @@ Plan* plan_create(size_t m, int window, double latency, size_t channels)
   if (e == cudaSuccess) e = cudaGetDevice(&p->device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->samples_in, cudaEventDisableTiming);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i)
   {
     e = cudaEventCreateWithFlags(&p->tile_ready[i], cudaEventDisableTiming);
