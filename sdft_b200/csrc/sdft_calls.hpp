@@ -314,9 +314,6 @@ bool do_isdft_nd(Plan* p, size_t n, const cx<F>** rows_in, T* samples)
   return true;
 }
 
-/* analysis -> synthesis in ONE kernel: the rows never exist in memory.  Every warp weighs and reduces
- * its bins per time step (SynthLane), per-group partial sums go to a scratch buffer and a small second
- * kernel adds the groups in order.  Long calls are cut into pieces that bound the scratch. */
 /* Synthesis weights with the window folded in (the adjoint of sdft_etc_convolve, sdft.h:350-402, mirror cells
  * of sdft.h:589-595 folded onto their source bins): for v[k] the per-bin factor of sdft_isdft (sdft.h:639-652),
  *     sum_k Re(v[k] * sum_j T[j] aux[k + j])  =  sum_b (A[b] Re(aux[b]) + B[b] Im(aux[b])).
