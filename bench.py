@@ -481,7 +481,10 @@ def run_b200_arm(args, rank, local_rank, world):
     del y
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
-        extras = other_configs(torch, SDFT, out, peak)
+        try:
+            extras = other_configs(torch, SDFT, out, peak)
+        except Exception as exc:      # the side measurements must never cost the headline line
+            extras = {"error": "%s: %s" % (type(exc).__name__, exc)}
     del out
     torch.cuda.empty_cache()
 
