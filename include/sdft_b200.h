@@ -134,6 +134,13 @@ SDFT_B200_API int sdft_b200_set_stream(sdft_b200_plan_t* plan, void* cuda_stream
 /* Scan chunk length in samples (multiple of 32, <= 1024); 0 = choose per call from n and m. */
 SDFT_B200_API int sdft_b200_set_chunk(sdft_b200_plan_t* plan, size_t chunk);
 
+/* Region of interest (the reference plans carry one, c/src/sdft/sdft.h:137-143, but have no setter: always all
+ * bins): from now on the rows written by *_sdft* and read by *_isdft* hold only bins [first, first + count),
+ * i.e. they are (nsamples, count) matrices; count = 0 restores the whole spectrum.  Bins outside the region
+ * still take part in the state update, they just cost no row bandwidth; *_isdft* of such rows sums the bins of
+ * the region only.  The fused round trip and convolve always work on the whole spectrum. */
+SDFT_B200_API int sdft_b200_set_roi(sdft_b200_plan_t* plan, size_t first, size_t count);
+
 SDFT_B200_API size_t sdft_b200_channels(const sdft_b200_plan_t* plan);
 SDFT_B200_API int sdft_b200_device(const sdft_b200_plan_t* plan);
 /* number of kernels this plan has launched so far (bench.py reports it as gpu_launches) */

@@ -41,6 +41,7 @@ UNTYPED = {
     "sdft_b200_synchronize": (_I, [_P]),
     "sdft_b200_set_stream": (_I, [_P, _P]),
     "sdft_b200_set_chunk": (_I, [_P, _SZ]),
+    "sdft_b200_set_roi": (_I, [_P, _SZ, _SZ]),
     "sdft_b200_channels": (_SZ, [_P]),
     "sdft_b200_device": (_I, [_P]),
     "sdft_b200_launch_count": (ctypes.c_ulonglong, [_P]),

@@ -154,6 +154,14 @@ extern "C" int sdft_b200_set_chunk(sdft_b200_plan_t* p, size_t chunk)
   return 0;
 }
 
+extern "C" int sdft_b200_set_roi(sdft_b200_plan_t* p, size_t first, size_t count)
+{
+  if (!p || first + count > p->m || (count == 0 && first != 0)) return SDFT_B200_ERR_ARG;
+  p->roi_first = first;
+  p->roi_count = (count == p->m) ? 0 : count;
+  return 0;
+}
+
 extern "C" int sdft_b200_set_profiling(sdft_b200_plan_t* p, int on)
 {
   if (!p) return SDFT_B200_ERR_ARG;

@@ -57,7 +57,7 @@ bool do_sdft(Plan* p, size_t n, const T* samples, cx<F>* dfts)
   bool ok = true;
   const T* x = stage_samples<T>(p, n, samples, &ok);
   if (!ok) return false;
-  const size_t m = p->m, ch = p->channels;
+  const size_t m = row_bins(p), ch = p->channels;   // bins per row: the region of interest
 
   if (classify(dfts) == kDevice)
   {
@@ -159,7 +159,7 @@ bool do_isdft(Plan* p, size_t n, const cx<F>* dfts, T* samples)
 {
   if (n == 0) return true;
   CU_TRY(p, cudaSetDevice(p->device));
-  const size_t m = p->m, ch = p->channels;
+  const size_t m = row_bins(p), ch = p->channels;   // bins per row: the region of interest
   const bool out_dev = classify(samples) == kDevice;
   T* y = samples;
   if (!out_dev)
@@ -264,7 +264,7 @@ bool do_sdft_nd(Plan* p, size_t n, const T* samples, cx<F>** rows_out)
   bool ok = true;
   const T* x = stage_samples<T>(p, n, samples, &ok);
   if (!ok) return false;
-  const size_t m = p->m, row_bytes = m * sizeof(cx<F>);
+  const size_t m = row_bins(p), row_bytes = m * sizeof(cx<F>);
   const size_t rows = tile_rows(p, n, row_bytes);
   if (!reserve(p, p->tile[0], rows * row_bytes)) return false;
   for (size_t t0 = 0; t0 < n; t0 += rows)
@@ -286,7 +286,7 @@ bool do_isdft_nd(Plan* p, size_t n, const cx<F>** rows_in, T* samples)
   if (n == 0) return true;
   if (p->channels != 1) { plan_fail(p, SDFT_B200_ERR_ARG, "isdft_nd on a batch plan", __FILE__, __LINE__); return false; }
   CU_TRY(p, cudaSetDevice(p->device));
-  const size_t m = p->m, row_bytes = m * sizeof(cx<F>);
+  const size_t m = row_bins(p), row_bytes = m * sizeof(cx<F>);
   const size_t rows = tile_rows(p, n, row_bytes);
   if (!reserve(p, p->tile[0], rows * row_bytes)) return false;
   const bool out_dev = classify(samples) == kDevice;

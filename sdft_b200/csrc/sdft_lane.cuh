@@ -95,7 +95,7 @@ struct EmitLane
 
   /* geometry of lane `lane` of warp-group `group`: first cell index (signed: the float halo reaches
    * below cell 0) and which of its cells are stored */
-  __device__ __forceinline__ int setup(unsigned group, unsigned lane, unsigned m)
+  __device__ __forceinline__ int setup(unsigned group, unsigned lane, unsigned m, unsigned roi_first, unsigned roi_end)
   {
     const int e0 = (int)(group * G::SPAN) + 2 - G::HALO + (int)(lane * G::CPL);
 #pragma unroll
@@ -103,7 +103,8 @@ struct EmitLane
     {
       const int slot = (int)lane * G::CPL + b;
       const int e = e0 + b;
-      ok[b] = (slot >= G::HALO) && (slot < G::WC - G::HALO) && (e >= 2) && (e < (int)m + 2);
+      ok[b] = (slot >= G::HALO) && (slot < G::WC - G::HALO) && (e >= 2) && (e < (int)m + 2) &&
+              (e >= (int)roi_first + 2) && (e < (int)roi_end + 2);      // bins outside the region of interest are not stored
     }
     return e0;
   }

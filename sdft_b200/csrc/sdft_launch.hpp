@@ -52,12 +52,16 @@ int choose_geo(const Plan* p, size_t n)
   return u < kNarrowBelow ? GEO_NARROW : GEO_WIDE;
 }
 
-/* 32-byte group stores need rows that start on a 32-byte boundary */
+/* bins per row handed to / taken from the caller */
+size_t row_bins(const Plan* p) { return p->roi_count ? p->roi_count : p->m; }
+
+/* 32-byte group stores need rows that start on a 32-byte boundary and a region of interest cut on group
+ * boundaries */
 template <typename F>
-bool can_vectorize(size_t m, const void* out, size_t out_stride)
+bool can_vectorize(const Plan* p, const void* out, size_t out_stride)
 {
   const size_t g = Geo<F, GEO_WIDE>::GROUP;
-  return (m % g == 0) && (((uintptr_t)out) % 32 == 0) && (out_stride % g == 0);
+  return (row_bins(p) % g == 0) && (p->roi_first % g == 0) && (((uintptr_t)out) % 32 == 0) && (out_stride % g == 0);
 }
 
 unsigned choose_chunk(const Plan* p, size_t n, int geo)
@@ -217,6 +221,8 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   a.cells = (unsigned)p->cells;
   a.out = out;
   a.out_channel_stride = out_stride;
+  a.roi_first = (unsigned)p->roi_first;
+  a.roi_count = (unsigned)row_bins(p);
   a.syn_ab = syn_ab;
   a.part = part;
   a.groups = groups;
@@ -239,7 +245,7 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   }
   else if (out)
   {
-    const bool vec = can_vectorize<F>(m, out, out_stride);
+    const bool vec = can_vectorize<F>(p, out, out_stride);
     prof_mark(p, 0);
     launch_chain<F, EMIT_ROWS>(p, a, vec, warps, geo);
     prof_mark(p, 0);
@@ -275,10 +281,10 @@ bool synthesis_device(Plan* p, size_t n, const cx<F>* dfts, size_t dft_stride, T
   prof_mark(p, 1);
   if (p->latency == 1)
     synth_kernel<T, F, true><<<grid, kSynthWarps * 32, 0, p->stream>>>(dfts, dft_stride, (const cx<F>*)p->tws, y,
-                                                                       y_stride, n, (unsigned)p->m);
+                                                                       y_stride, n, (unsigned)row_bins(p), (unsigned)p->roi_first);
   else
     synth_kernel<T, F, false><<<grid, kSynthWarps * 32, 0, p->stream>>>(dfts, dft_stride, (const cx<F>*)p->tws, y,
-                                                                        y_stride, n, (unsigned)p->m);
+                                                                        y_stride, n, (unsigned)row_bins(p), (unsigned)p->roi_first);
   prof_mark(p, 1);
   p->launches++;
   CU_TRY(p, cudaGetLastError());

@@ -44,6 +44,7 @@ struct sdft_b200_plan
   cudaEvent_t tile_free[2] = { nullptr, nullptr };
 
   size_t cursor = 0;
+  size_t roi_first = 0, roi_count = 0;   // region of interest of the rows (sdft.h:137-143); roi_count == 0: all m bins
   size_t forced_chunk = 0;
   unsigned forced_warps = 0;     // SDFT_B200_WARPS: warps per scan/emit CTA (0 = choose per plan geometry)
   int forced_geo = -1;           // SDFT_B200_GEO=wide|narrow: warp geometry (default: per call, choose_geo)

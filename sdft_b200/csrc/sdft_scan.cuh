@@ -74,8 +74,10 @@ template <typename F> struct ChainArgs
   unsigned channels;
   unsigned m;
   unsigned cells;
-  cx<F>* out;              // (channels, n, m) or nullptr
+  cx<F>* out;              // (channels, n, roi_count) or nullptr
   size_t out_channel_stride;
+  unsigned roi_first;      // region of interest: rows hold bins [roi_first, roi_first + roi_count) only (sdft.h:137-143)
+  unsigned roi_count;      // m for the whole spectrum
   const F* syn_ab;         // (m, 2) synthesis weights of Re / Im of every bin with the window folded in, EMIT_SYNTH only
   F* part;                 // (channels, groups, n) per-group partial sums of the fused synthesis
   unsigned groups;
@@ -409,7 +411,9 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   SDFT_B200_STAMP(1);   // deltas in shared memory
 
   EmitLane<F, WINDOW, VEC, GEO> L;
-  const int e0 = L.setup(group, lane, a.m);
+  const bool synth = (EMIT == EMIT_SYNTH_UNIT || EMIT == EMIT_SYNTH);       // the fused synthesis always sees every bin
+  const unsigned roi_first = synth ? 0u : a.roi_first, roi_end = synth ? a.m : a.roi_first + a.roi_count;
+  const int e0 = L.setup(group, lane, a.m, roi_first, roi_end);
   bool live[G::CPL];
   cx<F> zero;
   zero.r = (F)0; zero.i = (F)0;
@@ -608,8 +612,10 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   /* ---- phase C: replay from the carry and stream the rows out ---- */
   if (EMIT == EMIT_ROWS)
   {
-    const size_t row_stride = a.m;
-    L.dst = a.out + (size_t)ch * a.out_channel_stride + (size_t)cs.t0 * row_stride + ((long long)e0 - 2);
+    /* groups without a bin inside the region of interest have done their share (the carries): no rows */
+    if (group * (unsigned)G::SPAN >= roi_end || (group + 1u) * (unsigned)G::SPAN <= roi_first) return;
+    const size_t row_stride = a.roi_count;
+    L.dst = a.out + (size_t)ch * a.out_channel_stride + (size_t)cs.t0 * row_stride + ((long long)e0 - 2 - (long long)roi_first);
     if constexpr (SLIDE)
     {
       /* anchor the demodulated spectrum at the carry (L.ph still holds the chunk's starting phase),

@@ -47,8 +47,13 @@ __global__ void __launch_bounds__(kSynthWarps * 32) synth_kernel(const cx<F>* __
                                                                  size_t dft_channel_stride,
                                                                  const cx<F>* __restrict__ tws,
                                                                  T* __restrict__ samples, size_t sample_stride,
-                                                                 unsigned long long n, unsigned m)
+                                                                 unsigned long long n, unsigned m_all, unsigned roi_first)
 {
+  /* rows hold `m_all` bins starting at bin `roi_first` (the whole spectrum: roi_first = 0); shifting the
+   * weight table keeps the loops below unchanged, the sign of the latency-1 sum follows the absolute bin */
+  const unsigned m = m_all;
+  tws += roi_first;
+  const bool flip = (roi_first & 1u) != 0;
   const unsigned ch = blockIdx.y;
   const unsigned lane = threadIdx.x & 31;
   const unsigned long long warps = (unsigned long long)gridDim.x * kSynthWarps;
@@ -97,6 +102,7 @@ __global__ void __launch_bounds__(kSynthWarps * 32) synth_kernel(const cx<F>* __
           }
         }
         F s = (s0 + s1) + (s2 + s3);
+        if (UNIT_LATENCY && flip) s = -s;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         if (lane == 0) y[row] = (T)(s * (F)2);
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(kSynthWarps * 32) synth_kernel(const cx<F>* __
     }
     F s = (s0 + s1) + (s2 + s3);
     /* k = lane + 32 i has the parity of the lane: apply (-1)^k once per lane */
-    if (UNIT_LATENCY && (lane & 1)) s = -s;
+    if (UNIT_LATENCY && (((lane & 1) != 0) != flip)) s = -s;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     if (lane == 0) y[row] = (T)(s * (F)2);

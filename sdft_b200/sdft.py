@@ -58,6 +58,7 @@ class SDFT:
         self.latency = latency
         self.td, self.fd = td, fd
         self.channels = int(channels)
+        self._rowlen = self.size        # bins per row: the region of interest, see set_roi
         self._sfx = td + fd
         self._lib = _lib.load()
         self._f = lambda name: _lib.fn(self._lib, self._sfx, name)
@@ -109,13 +110,13 @@ class SDFT:
             import torch
             x = samples.to(torch.float32 if self.td == "f32" else torch.float64).contiguous()
             n = x.shape[-1]
-            shape = (n, self.size) if self.channels == 1 else (self.channels, n, self.size)
+            shape = (n, self._rowlen) if self.channels == 1 else (self.channels, n, self._rowlen)
             fdt = torch.complex64 if self.fd == "f32" else torch.complex128
             if out is None:
                 out = torch.empty(shape, dtype=fdt, device=x.device)
             else:
-                assert out.is_cuda and out.is_contiguous() and out.dtype == fdt and out.numel() >= n * self.size * self.channels
-                out = out.view(-1)[: n * self.size * self.channels].view(shape)
+                assert out.is_cuda and out.is_contiguous() and out.dtype == fdt and out.numel() >= n * self._rowlen * self.channels
+                out = out.view(-1)[: n * self._rowlen * self.channels].view(shape)
             self._use_torch_stream()
             self._f("sdft_batch")(self._h, n, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()))
             self._check()
@@ -126,7 +127,7 @@ class SDFT:
         else:
             assert x.ndim == 2 and x.shape[0] == self.channels, f'Expected (channels,samples), got {x.shape}!'
         n = x.shape[-1]
-        shape = (n, self.size) if self.channels == 1 else (self.channels, n, self.size)
+        shape = (n, self._rowlen) if self.channels == 1 else (self.channels, n, self._rowlen)
         out = np.empty(shape, _NP_FD[self.fd])
         self._f("sdft_batch")(self._h, n, x.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p))
         self._check()
@@ -146,7 +147,7 @@ class SDFT:
             self._check()
             return y
         d = np.ascontiguousarray(np.atleast_2d(dfts), dtype=_NP_FD[self.fd])
-        assert d.shape[-1] == self.size, f'Expected (samples,frequencies), got {d.shape}!'
+        assert d.shape[-1] == self._rowlen, f'Expected (samples,frequencies), got {d.shape}!'
         n = d.shape[-2]
         shape = (n,) if self.channels == 1 else (self.channels, n)
         y = np.empty(shape, _NP_TD[self.td])
@@ -250,6 +251,14 @@ class SDFT:
             ap = a.ctypes.data_as(ctypes.c_void_p)
         self._lib.sdft_b200_set_state(self._h, channel, int(cursor), hp, ap)
         self._check()
+
+    def set_roi(self, first=0, count=0):
+        """Region of interest: from now on ``sdft`` returns and ``isdft`` takes rows of the bins
+        [first, first + count) only; count=0 restores the whole spectrum.  Bins outside still take part in the
+        state update, they just cost no row bandwidth."""
+        if self._lib.sdft_b200_set_roi(self._h, int(first), int(count)):
+            raise ValueError("sdft_b200: region of interest outside [0, %d)" % self.size)
+        self._rowlen = int(count) if 0 < int(count) < self.size else self.size
 
     def set_chunk(self, chunk):
         self._lib.sdft_b200_set_chunk(self._h, int(chunk))

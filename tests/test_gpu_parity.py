@@ -298,6 +298,40 @@ def test_convolve_matches_reference_python_class(SDFT, fd, golden_dir):
             assert np.array_equal(_bits(got_dev), _bits(got))
 
 
+@pytest.mark.parametrize("td,fd", [("f32", "f64"), ("f32", "f32")])
+@pytest.mark.parametrize("window", ["hann", "blackman"])
+def test_region_of_interest_rows(SDFT, td, fd, window, monkeypatch):
+    """sdft_b200_set_roi: rows of a sub-band are the corresponding columns of the full rows, bit for bit
+    (group-aligned and unaligned regions, both warp geometries, host and device outputs), the plan state is
+    unaffected, and isdft of such rows is the band-limited sum over the region."""
+    import torch
+    from oracle import Oracle
+    rng = np.random.default_rng(61)
+    m = 300
+    x = rng.uniform(-1, 1, 2 * m + 77).astype(np.float32)
+    for geo in ("wide", "narrow"):
+        monkeypatch.setenv("SDFT_B200_GEO", geo)
+        full = SDFT(m, window, 0.5, td=td, fd=fd)
+        want = np.concatenate([full.sdft(x[:200]), full.sdft(x[200:])])      # same call split as below
+        for first, count in ((0, 64), (8, 120), (37, 101), (m - 5, 5), (123, 1), (0, m)):
+            sub = SDFT(m, window, 0.5, td=td, fd=fd)
+            sub.set_roi(first, count)
+            got = sub.sdft(x[:200])
+            got2 = sub.sdft(torch.from_numpy(x[200:]).cuda()).cpu().numpy()
+            got = np.concatenate([got, got2])
+            assert got.shape == (x.size, count)
+            assert np.array_equal(_bits(got), _bits(np.ascontiguousarray(want[:, first:first + count]))), (geo, first, count)
+            for a, b in zip(sub.state()[1:3], full.state()[1:3]):
+                assert np.array_equal(_bits(a), _bits(b))
+            # band-limited synthesis: the oracle's isdft of rows that are zero outside the region
+            o = Oracle(td, fd, m, window, 0.5)
+            masked = np.zeros_like(want)
+            masked[:, first:first + count] = want[:, first:first + count]
+            y_want = o.isdft(masked).astype(np.float64)
+            y_got = sub.isdft(got).astype(np.float64)
+            assert np.abs(y_got - y_want).max() <= (2e-6 if fd == "f64" else 2e-4) * max(1.0, np.abs(y_want).max())
+
+
 def test_cuda_array_interface_inputs(SDFT):
     """Anything that exposes __cuda_array_interface__ is taken zero-copy (CuPy, Numba, ...)."""
     import torch

@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--stream", type=int, default=0, help="samples per call; times --calls back-to-back calls")
     ap.add_argument("--calls", type=int, default=1024)
     ap.add_argument("--host", action="store_true", help="streaming with pinned host samples in / host samples out (roundtrip)")
+    ap.add_argument("--roi", default="", help="first,count: rows hold only that region of interest")
     ap.add_argument("--hostrows", default="", help="sdft_n + isdft_n with HOST rows: 'pageable' (numpy) or 'pinned'")
     a = ap.parse_args()
     torch.cuda.set_device(0)
@@ -54,6 +55,11 @@ def main():
     if a.chunk:
         g.set_chunk(a.chunk)
     g._use_torch_stream()
+    rowlen = a.m
+    if a.roi:
+        first, count = (int(v) for v in a.roi.split(","))
+        g.set_roi(first, count)
+        rowlen = count
     tdt = torch.float32 if a.td == "f32" else torch.float64
     fdt = torch.complex64 if a.fd == "f32" else torch.complex128
     fdb = 16 if a.fd == "f64" else 8
@@ -129,11 +135,11 @@ def main():
             res.update({"mode": "roundtrip-device", "n": n, "ms": ms, "bin_updates_per_s": ch * n * a.m / (ms * 1e-3),
                         "samples_per_s": ch * n / (ms * 1e-3)})
         else:
-            out = torch.empty((ch * n, a.m), dtype=fdt, device="cuda")
+            out = torch.empty((ch * n, rowlen), dtype=fdt, device="cuda")
             op = ctypes.c_void_p(out.data_ptr())
             ms = event_time(lambda: g._f("sdft_batch")(g._h, n, xp, op), a.reps)
             res.update({"mode": "analysis", "n": n, "ms": ms, "bin_updates_per_s": ch * n * a.m / (ms * 1e-3),
-                        "GBps": ch * n * a.m * fdb / (ms * 1e-3) / 1e9})
+                        "GBps": ch * n * rowlen * fdb / (ms * 1e-3) / 1e9, "roi": a.roi})
             if a.synth:
                 y = torch.empty(ch * n, device="cuda", dtype=tdt)
                 yp = ctypes.c_void_p(y.data_ptr())
