@@ -21,15 +21,19 @@ namespace sdftb200
  *     32-byte groups (2 double or 4 float bins) with an evict-first policy when the row pitch allows
  *     it, else bin by bin.
  * ---------------------------------------------------------------------------------------------- */
+/* cache policy of the row stores: rows are written once and not read again by this kernel */
+#ifndef SDFT_B200_STORE_POLICY
+#define SDFT_B200_STORE_POLICY ".L1::no_allocate.L2::evict_first"
+#endif
 /* one 32-byte group: 2 double bins or 4 float bins */
 __device__ __forceinline__ void store_group(cx<double>* dst, const cx<double>* y)
 {
-  asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.f64 [%0], {%1, %2, %3, %4};"
+  asm volatile("st.global" SDFT_B200_STORE_POLICY ".v4.f64 [%0], {%1, %2, %3, %4};"
                :: "l"(dst), "d"(y[0].r), "d"(y[0].i), "d"(y[1].r), "d"(y[1].i));
 }
 __device__ __forceinline__ void store_group(cx<float>* dst, const cx<float>* y)
 {
-  asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+  asm volatile("st.global" SDFT_B200_STORE_POLICY ".v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                :: "l"(dst), "f"(y[0].r), "f"(y[0].i), "f"(y[1].r), "f"(y[1].i),
                   "f"(y[2].r), "f"(y[2].i), "f"(y[3].r), "f"(y[3].i));
 }
