@@ -110,6 +110,14 @@ def test_double_modulated_mode(SDFT, window, monkeypatch):
             assert rel_err(a, b) <= 1e-10
         assert rel_err(fast.state()[2], o.state()[2]) <= 1e-9
         assert rel_err(exact.state()[2], o.state()[2]) <= 1e-12
+        # the fused round trip and the state-only pass in the literal mode as well
+        x = rng.uniform(-1, 1, 2 * m + 50).astype(np.float32)
+        want_y = o.roundtrip(x)
+        assert np.abs(exact.roundtrip(x) - want_y).max() <= 2e-6
+        x2 = rng.uniform(-1, 1, 90).astype(np.float32)
+        exact.advance(x2)
+        o.advance(x2)
+        assert rel_err(exact.state()[2], o.state()[2]) <= 1e-12
 
 
 def test_float_rows_bit_exact_within_a_chunk(SDFT):
