@@ -15,6 +15,7 @@
 #include "sdft_kernels.cuh"
 #include "sdft_host_copy.hpp"
 #include "sdft_tables.hpp"
+#include "sdft_weights.hpp"
 
 #include <vector>
 #include <cmath>

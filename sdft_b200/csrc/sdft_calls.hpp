@@ -314,54 +314,13 @@ bool do_isdft_nd(Plan* p, size_t n, const cx<F>** rows_in, T* samples)
   return true;
 }
 
-/* Synthesis weights with the window folded in (the adjoint of sdft_etc_convolve, sdft.h:350-402, mirror cells
- * of sdft.h:589-595 folded onto their source bins): for v[k] the per-bin factor of sdft_isdft (sdft.h:639-652),
- *     sum_k Re(v[k] * sum_j T[j] aux[k + j])  =  sum_b (A[b] Re(aux[b]) + B[b] Im(aux[b])).
- * `ab` receives (A, B) per bin; returns true when every B is zero (latency 1 without gains). */
+/* Synthesis weights with the window folded in: see sdft_weights.hpp */
 template <typename F>
 bool make_synth_weights(const Plan* p, const std::vector<cx<double>>& v, std::vector<F>& ab)
 {
-  const long m = (long)p->m;
-  const WindowConst<F> wc = make_window_const<F>(p->m, p->window);
-  const double w = (double)wc.w;
-  double taps[5] = { 0, 0, w, 0, 0 };                       // T[-2 .. +2]
-  if (p->window == 1) { taps[2] = 0.5 * w; taps[1] = taps[3] = -0.25 * w; }
-  if (p->window == 2) { taps[2] = (double)(F)0.54 * w; taps[1] = taps[3] = -(double)(F)0.23 * w; }
-  if (p->window == 3) { taps[2] = (double)(F)0.42 * w; taps[1] = taps[3] = -(double)(F)0.25 * w; taps[0] = taps[4] = (double)(F)0.04 * w; }
-  std::vector<double> A(m, 0.0), B(m, 0.0);
-  for (long k = 0; k < m; ++k)
-  {
-    for (int j = -2; j <= 2; ++j)
-    {
-      const double t = taps[j + 2];
-      if (t == 0.0) continue;
-      long cell = k + 2 + j, bin = cell - 2;
-      bool conj = false;
-      if (cell < 2 || cell >= m + 2)
-      {
-        int q = -1;
-        for (int i = 0; i < 4; ++i)
-          if (p->mirrors.cell[i] == (int)cell) q = i;
-        if (q < 0 || p->mirrors.src[q] < 0) continue;       // a cell that is always zero
-        bin = p->mirrors.src[q];
-        conj = p->mirrors.conj[q] != 0;
-      }
-      /* Re(v a) = vr ar - vi ai ;  Re(v conj(a)) = vr ar + vi ai */
-      A[bin] += t * v[k].r;
-      B[bin] += (conj ? +t : -t) * v[k].i;
-    }
-  }
-  /* double fast mode replays pre-scaled spectra (the window weight is folded into the deltas) */
-  const double unscale = 1.0 / p->prescale;
-  ab.resize(2 * (size_t)m);
-  bool unit = true;
-  for (long b = 0; b < m; ++b)
-  {
-    ab[2 * b] = (F)(A[b] * unscale);
-    ab[2 * b + 1] = (F)(B[b] * unscale);
-    if (ab[2 * b + 1] != (F)0) unit = false;
-  }
-  return unit;
+  std::vector<double> vr(p->m), vi(p->m);
+  for (size_t k = 0; k < p->m; ++k) { vr[k] = v[k].r; vi[k] = v[k].i; }
+  return synth_weights<F>(p->m, p->window, p->mirrors, p->prescale, vr.data(), vi.data(), ab);
 }
 
 /* the per-bin factor of sdft_isdft: (-1)^k for latency 1 (exact compare, sdft.h:639), tws[k] otherwise,

@@ -10,15 +10,6 @@
  * ---------------------------------------------------------------------------------------------- */
 enum TypeId { kF32 = 0, kF64 = 1 };
 
-/* mirror cells (sdft.h:589-595): source bin (or -1 = always zero) and whether the copy is conjugated;
- * only used on the host to lay out the extended twiddle table */
-struct MirrorMap
-{
-  int cell[4];
-  int src[4];
-  int conj[4];
-};
-
 struct Buffer
 {
   void* ptr = nullptr;
@@ -124,34 +115,6 @@ size_t env_size(const char* name, size_t fallback)
   char* end = nullptr;
   const unsigned long long x = strtoull(v, &end, 10);
   return (end && end != v) ? (size_t)x : fallback;
-}
-
-/* mirror cells resolved from the assignment order of sdft.h:589-595 */
-MirrorMap make_mirrors(size_t m)
-{
-  MirrorMap mm;
-  mm.cell[0] = 0; mm.cell[1] = 1; mm.cell[2] = (int)m + 2; mm.cell[3] = (int)m + 3;
-  if (m >= 3)
-  {
-    mm.src[0] = 2; mm.conj[0] = 1;
-    mm.src[1] = 1; mm.conj[1] = 1;
-    mm.src[2] = (int)m - 2; mm.conj[2] = 1;
-    mm.src[3] = (int)m - 3; mm.conj[3] = 1;
-  }
-  else if (m == 2)
-  {
-    /* aux[1]=conj(bin1); aux[4]=conj(bin0); aux[0]=conj(aux[4])=bin0; aux[5]=conj(aux[1])=bin1 */
-    mm.src[0] = 0; mm.conj[0] = 0;
-    mm.src[1] = 1; mm.conj[1] = 1;
-    mm.src[2] = 0; mm.conj[2] = 1;
-    mm.src[3] = 1; mm.conj[3] = 0;
-  }
-  else
-  {
-    /* m == 1: each mirror cell only ever copies itself through its partner and stays zero */
-    for (int q = 0; q < 4; ++q) { mm.src[q] = -1; mm.conj[q] = 0; }
-  }
-  return mm;
 }
 
 /* ------------------------------------------------------------------------------------------------
