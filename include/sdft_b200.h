@@ -15,6 +15,11 @@
  * Device pointers: nothing is copied, work is queued on the plan's stream and the call returns at once
  * (stream-ordered; see sdft_b200_synchronize / sdft_b200_set_stream).
  *
+ * Aliasing: *_roundtrip* may run in place (in == out); partially overlapping DEVICE ranges, and any overlap
+ * of the DEVICE in/out of *_convolve_n, are rejected (error 10002 on the plan).  A call that returns while
+ * its kernels are queued (device destination) has always finished reading the caller's HOST inputs.
+ * Calls leave the calling thread's current CUDA device unchanged.
+ *
  * There is no CPU fallback: if no CUDA device or no sm_100a image is usable, *_alloc* returns NULL and
  * sdft_b200_last_error_string(NULL) says why.
  *

@@ -54,7 +54,7 @@ using namespace sdftb200;
   extern "C" void sdft_b200_##SFX##_free(sdft_b200_plan_t* p) { plan_destroy(p); }                              \
   extern "C" void sdft_b200_##SFX##_reset(sdft_b200_plan_t* p)                                                  \
   {                                                                                                             \
-    if (typed<TD, FD>(p, "sdft_reset: plan type mismatch")) plan_reset<TD, FD>(p);                              \
+    if (typed<TD, FD>(p, "sdft_reset: plan type mismatch")) { DeviceGuard on_device(p->device); plan_reset<TD, FD>(p); } \
   }                                                                                                             \
   extern "C" size_t sdft_b200_##SFX##_size(const sdft_b200_plan_t* p) { return p ? p->m : 0; }                  \
   extern "C" int sdft_b200_##SFX##_window(const sdft_b200_plan_t* p) { return p ? p->window : 0; }              \
@@ -127,7 +127,7 @@ extern "C" const char* sdft_b200_last_error_string(const sdft_b200_plan_t* p)
 extern "C" int sdft_b200_synchronize(sdft_b200_plan_t* p)
 {
   if (!p) return SDFT_B200_ERR_ARG;
-  cudaSetDevice(p->device);
+  DeviceGuard on_device(p->device);
   cudaError_t e = cudaStreamSynchronize(p->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(p->copy_stream);
   unsigned ctl[2] = { 0, 0 };
@@ -142,7 +142,7 @@ extern "C" int sdft_b200_set_stream(sdft_b200_plan_t* p, void* cuda_stream)
   if (!p) return SDFT_B200_ERR_ARG;
   cudaStream_t next = (cuda_stream == (void*)-1) ? p->own_stream : (cudaStream_t)cuda_stream;
   if (next == p->stream) return p->status;
-  cudaSetDevice(p->device);
+  DeviceGuard on_device(p->device);
   cudaStreamSynchronize(p->stream);   // work queued on the old stream must not race with the new one
   p->stream = next;
   return p->status;
@@ -174,7 +174,7 @@ extern "C" double sdft_b200_kernel_ms(sdft_b200_plan_t* p, int which, unsigned l
 {
   if (launches) *launches = 0;
   if (!p || which < 0 || which > 1) return 0.0;
-  cudaSetDevice(p->device);
+  DeviceGuard on_device(p->device);
   std::vector<cudaEvent_t>& ev = p->prof_events[which];
   double total = 0.0;
   if (!ev.empty()) cudaEventSynchronize(ev.back());
@@ -193,7 +193,7 @@ extern "C" double sdft_b200_kernel_ms(sdft_b200_plan_t* p, int which, unsigned l
 extern "C" size_t sdft_b200_debug_trace(sdft_b200_plan_t* p, unsigned long long* stamps, size_t max_items)
 {
   if (!p || !p->trace.ptr || !stamps) return 0;
-  cudaSetDevice(p->device);
+  DeviceGuard on_device(p->device);
   cudaStreamSynchronize(p->stream);
   const size_t items = p->trace_items < max_items ? p->trace_items : max_items;
   if (cudaMemcpy(stamps, p->trace.ptr, items * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
@@ -211,7 +211,7 @@ extern "C" unsigned long long sdft_b200_launch_count(const sdft_b200_plan_t* p) 
 extern "C" int sdft_b200_get_twiddles(sdft_b200_plan_t* p, void* analysis, void* synthesis)
 {
   if (!p) return SDFT_B200_ERR_ARG;
-  cudaSetDevice(p->device);
+  DeviceGuard on_device(p->device);
   const size_t cbytes = (p->fd == kF32) ? sizeof(cx<float>) : sizeof(cx<double>);
   cudaError_t e = cudaStreamSynchronize(p->stream);
   if (e == cudaSuccess) e = cudaMemcpy(analysis, (char*)p->tw_ext + 2 * cbytes, p->m * cbytes, cudaMemcpyDeviceToHost);
@@ -224,7 +224,7 @@ extern "C" int sdft_b200_get_state(sdft_b200_plan_t* p, size_t channel, size_t* 
                                    void* accumulators, void* phase)
 {
   if (!p || channel >= p->channels) return SDFT_B200_ERR_ARG;
-  cudaSetDevice(p->device);
+  DeviceGuard on_device(p->device);
   const size_t cbytes = (p->fd == kF32) ? sizeof(cx<float>) : sizeof(cx<double>);
   const size_t tbytes = (p->td == kF32) ? sizeof(float) : sizeof(double);
   cudaError_t e = cudaStreamSynchronize(p->stream);
@@ -266,7 +266,7 @@ extern "C" int sdft_b200_set_state(sdft_b200_plan_t* p, size_t channel, size_t c
                                    const void* accumulators)
 {
   if (!p || channel >= p->channels || cursor >= 2 * p->m) return SDFT_B200_ERR_ARG;
-  cudaSetDevice(p->device);
+  DeviceGuard on_device(p->device);
   const size_t cbytes = (p->fd == kF32) ? sizeof(cx<float>) : sizeof(cx<double>);
   const size_t tbytes = (p->td == kF32) ? sizeof(float) : sizeof(double);
   cudaError_t e = cudaStreamSynchronize(p->stream);

@@ -12,6 +12,13 @@ namespace
 /* ------------------------------------------------------------------------------------------------
  * host/device pointer plumbing
  * ---------------------------------------------------------------------------------------------- */
+/* do two byte ranges share an address? */
+bool overlaps(const void* a, size_t abytes, const void* b, size_t bbytes)
+{
+  const uintptr_t a0 = (uintptr_t)a, b0 = (uintptr_t)b;
+  return a0 < b0 + bbytes && b0 < a0 + abytes;
+}
+
 size_t tile_rows(const Plan* p, size_t n, size_t row_bytes)
 {
   size_t rows = p->tile_bytes / (row_bytes * p->channels);
@@ -53,7 +60,7 @@ template <typename T, typename F>
 bool do_sdft(Plan* p, size_t n, const T* samples, cx<F>* dfts)
 {
   if (n == 0) return true;
-  CU_TRY(p, cudaSetDevice(p->device));
+  DeviceGuard on_device(p->device);
   bool ok = true;
   const T* x = stage_samples<T>(p, n, samples, &ok);
   if (!ok) return false;
@@ -144,7 +151,7 @@ template <typename T, typename F>
 bool do_advance(Plan* p, size_t n, const T* samples)
 {
   if (n == 0) return true;
-  CU_TRY(p, cudaSetDevice(p->device));
+  DeviceGuard on_device(p->device);
   bool ok = true;
   const bool host = classify(samples) != kDevice;
   const T* x = stage_samples<T>(p, n, samples, &ok);
@@ -158,7 +165,7 @@ template <typename T, typename F>
 bool do_isdft(Plan* p, size_t n, const cx<F>* dfts, T* samples)
 {
   if (n == 0) return true;
-  CU_TRY(p, cudaSetDevice(p->device));
+  DeviceGuard on_device(p->device);
   const size_t m = row_bins(p), ch = p->channels;   // bins per row: the region of interest
   const bool out_dev = classify(samples) == kDevice;
   T* y = samples;
@@ -251,6 +258,12 @@ bool do_isdft(Plan* p, size_t n, const cx<F>* dfts, T* samples)
     CU_TRY(p, cudaMemcpyAsync(samples, y, ch * n * sizeof(T), cudaMemcpyDeviceToHost, p->stream));
     CU_TRY(p, cudaStreamSynchronize(p->stream));
   }
+  else if (classify(dfts) != kDevice)
+  {
+    /* device destination: the call returns with its kernels still queued, but the caller's HOST rows have
+     * been read completely (same rule as release_samples for the analysis) */
+    CU_TRY(p, cudaStreamSynchronize(p->copy_stream));
+  }
   return true;
 }
 
@@ -260,7 +273,7 @@ bool do_sdft_nd(Plan* p, size_t n, const T* samples, cx<F>** rows_out)
 {
   if (n == 0) return true;
   if (p->channels != 1) { plan_fail(p, SDFT_B200_ERR_ARG, "sdft_nd on a batch plan", __FILE__, __LINE__); return false; }
-  CU_TRY(p, cudaSetDevice(p->device));
+  DeviceGuard on_device(p->device);
   bool ok = true;
   const T* x = stage_samples<T>(p, n, samples, &ok);
   if (!ok) return false;
@@ -285,7 +298,7 @@ bool do_isdft_nd(Plan* p, size_t n, const cx<F>** rows_in, T* samples)
 {
   if (n == 0) return true;
   if (p->channels != 1) { plan_fail(p, SDFT_B200_ERR_ARG, "isdft_nd on a batch plan", __FILE__, __LINE__); return false; }
-  CU_TRY(p, cudaSetDevice(p->device));
+  DeviceGuard on_device(p->device);
   const size_t m = row_bins(p), row_bytes = m * sizeof(cx<F>);
   const size_t rows = tile_rows(p, n, row_bytes);
   if (!reserve(p, p->tile[0], rows * row_bytes)) return false;
@@ -358,7 +371,7 @@ template <typename T, typename F>
 bool do_roundtrip(Plan* p, size_t n, const T* in, T* out, const cx<F>* gains = nullptr)
 {
   if (n == 0) return true;
-  CU_TRY(p, cudaSetDevice(p->device));
+  DeviceGuard on_device(p->device);
   const size_t m = p->m;
   const F* syn_ab = nullptr;
   bool syn_unit = false;
@@ -385,6 +398,14 @@ bool do_roundtrip(Plan* p, size_t n, const T* in, T* out, const cx<F>* gains = n
   {
     syn_ab = (const F*)p->syn_ab.ptr;
     syn_unit = p->syn_ab_unit;
+  }
+  /* in == out (processing a buffer in place) is fine: every piece reads its own samples before its finish
+   * kernel writes them; partially overlapping device ranges are not */
+  if (in != out && classify(in) == kDevice && classify(out) == kDevice &&
+      overlaps(in, p->channels * n * sizeof(T), out, p->channels * n * sizeof(T)))
+  {
+    plan_fail(p, SDFT_B200_ERR_ARG, "roundtrip: in and out overlap without being the same buffer", __FILE__, __LINE__);
+    return false;
   }
   bool ok = true;
   const T* x = stage_samples<T>(p, n, in, &ok);
@@ -428,7 +449,7 @@ template <typename F>
 bool do_convolve(Plan* p, size_t n, const cx<F>* in, cx<F>* out)
 {
   if (n == 0) return true;
-  CU_TRY(p, cudaSetDevice(p->device));
+  DeviceGuard on_device(p->device);
   const size_t m = p->m, ch = p->channels;
   const int need = (p->window == 3) ? 3 : ((p->window == 0) ? 1 : 2);
   if ((int)m < need)
@@ -438,6 +459,12 @@ bool do_convolve(Plan* p, size_t n, const cx<F>* in, cx<F>* out)
   }
   const size_t bytes = ch * n * m * sizeof(cx<F>);
   const bool in_dev = classify(in) == kDevice, out_dev = classify(out) == kDevice;
+  if (in_dev && out_dev && overlaps(in, bytes, out, bytes))
+  {
+    /* every output bin reads its neighbours k-2 .. k+2 of the input row: not an in-place operation */
+    plan_fail(p, SDFT_B200_ERR_ARG, "convolve: in and out must not overlap in device memory", __FILE__, __LINE__);
+    return false;
+  }
   const cx<F>* src = in;
   cx<F>* dst = out;
   if (!in_dev)

@@ -228,6 +228,12 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   a.groups = groups;
   a.stage_rows = (geo == GEO_NARROW) ? scan_stage_rows<F, GEO_NARROW>(warps, chunk) : scan_stage_rows<F, GEO_WIDE>(warps, chunk);
   a.win = make_window_const<F>(p->m, p->window);   // sdft.h:422, :371
+  for (int q = 0; q < 4; ++q)
+  {
+    a.mir_cell[q] = p->mirrors.cell[q];
+    a.mir_src[q] = p->mirrors.src[q] < 0 ? -1 : p->mirrors.src[q] + 2;
+    a.mir_conj[q] = p->mirrors.conj[q];
+  }
   a.trace = nullptr;
 #if defined(SDFT_B200_TRACE)
   if (reserve(p, p->trace, items * 8 * sizeof(unsigned long long)))

@@ -86,6 +86,26 @@ typedef sdft_b200_plan Plan;
 namespace
 {
 
+/* Every entry point works on the plan's device and leaves the calling thread's current device as it found
+ * it: in a multi-GPU process (torch, one thread driving several plans) a library call must not silently
+ * move the caller's later allocations and launches to another GPU. */
+struct DeviceGuard
+{
+  int prev = -1;
+  bool moved = false;
+  explicit DeviceGuard(int device)
+  {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    if (prev != device) moved = (cudaSetDevice(device) == cudaSuccess);
+  }
+  ~DeviceGuard()
+  {
+    if (moved && prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 enum { SDFT_B200_ERR_TYPE = 10001, SDFT_B200_ERR_ARG = 10002, SDFT_B200_ERR_NODEVICE = 10003, SDFT_B200_ERR_CHAIN = 10004 };
 
 thread_local int g_alloc_error = 0;
@@ -262,7 +282,7 @@ bool plan_reset(Plan* p)
 void plan_destroy(Plan* p)
 {
   if (!p) return;
-  cudaSetDevice(p->device);
+  DeviceGuard on_device(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
   void* ptrs[] = { p->tw_ext, p->tws, p->f0, p->history[0], p->history[1], p->acc_state[0], p->acc_state[1], p->phase_scratch,
@@ -345,9 +365,13 @@ Plan* plan_create(size_t m, int window, double latency, size_t channels)
 
   bool ok = true;
   const long dev_env = (long)env_size("SDFT_B200_DEVICE", (size_t)-1);
-  cudaError_t e = cudaSuccess;
-  if (dev_env >= 0) e = cudaSetDevice((int)dev_env);
-  if (e == cudaSuccess) e = cudaGetDevice(&p->device);
+  cudaError_t e = cudaGetDevice(&p->device);
+  if (e == cudaSuccess && dev_env >= 0)
+  {
+    if (dev_env < count) p->device = (int)dev_env;
+    else e = cudaErrorInvalidDevice;
+  }
+  DeviceGuard on_device(p->device);     // SDFT_B200_DEVICE places the plan, it does not move the caller
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->samples_in, cudaEventDisableTiming);

@@ -83,6 +83,9 @@ template <typename F> struct ChainArgs
   unsigned groups;
   unsigned stage_rows;     // rows of look-back staging in shared memory (scan_stage_rows)
   WindowConst<F> win;
+  int mir_cell[4];         // the four mirror cells (sdft.h:589-595) ...
+  int mir_src[4];          // ... the CELL each one copies (-1: always zero) ...
+  int mir_conj[4];         // ... and whether the copy is conjugated; read by the halo-free kernels only
   unsigned long long* trace;   // -DSDFT_B200_TRACE builds only: 8 %globaltimer stamps per CTA, else unused
 };
 
@@ -582,9 +585,34 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
     {
       /* accumulators the next call starts with (sdft.h:157) */
       cx<F>* ao = a.acc_out + (size_t)ch * a.cells;
+      if constexpr (G::HALO == 0)
+      {
+        /* halo-free geometry (boxcar rows, fused synthesis on a plan of ANY window): no warp owns mirror
+         * cells 0 and 1, and cells m+2, m+3 only when m is not a multiple of the warp width.  A later
+         * windowed call reads all four as its carry, so they are written here as what they are by
+         * construction: the exact (conjugate) copy of their source bin. */
 #pragma unroll
-      for (int b = 0; b < G::CPL; ++b)
-        if (live[b]) ao[e0 + b] = agg[b];
+        for (int b = 0; b < G::CPL; ++b)
+        {
+          const int e = e0 + b;
+          if (e < 2 || e >= (int)a.m + 2) continue;
+          ao[e] = agg[b];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (a.mir_src[q] == e)
+            {
+              cx<F> v = agg[b];
+              if (a.mir_conj[q]) v.i = -v.i;
+              ao[a.mir_cell[q]] = v;
+            }
+        }
+      }
+      else
+      {
+#pragma unroll
+        for (int b = 0; b < G::CPL; ++b)
+          if (live[b]) ao[e0 + b] = agg[b];
+      }
     }
 #pragma unroll
     for (int b = 0; b < G::CPL; ++b) L.acc[b] = carry[b];

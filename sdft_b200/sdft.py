@@ -82,9 +82,23 @@ class SDFT:
         if code:
             raise RuntimeError("sdft_b200: %s" % self._lib.sdft_b200_last_error_string(self._h).decode())
 
-    def _use_torch_stream(self):
+    def _use_torch_stream(self, like=None):
+        """Queue on torch's current stream OF THE PLAN'S DEVICE; `like` (a CUDA tensor handed to the call)
+        must live on that device -- the kernels would otherwise dereference another GPU's memory."""
         import torch
-        self._lib.sdft_b200_set_stream(self._h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        dev = int(self._lib.sdft_b200_device(self._h))
+        if like is not None:
+            assert like.device.index == dev, f'Expected a tensor on cuda:{dev} (the plan\'s device), got {like.device}!'
+        self._lib.sdft_b200_set_stream(self._h, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+
+    def _check_batch(self, shape, trailing):
+        """(channels, samples[, bins]) on batch plans, (samples[, bins]) otherwise."""
+        if self.channels == 1:
+            assert len(shape) == trailing or (len(shape) == trailing + 1 and shape[0] == 1), \
+                f'Expected {trailing}D input for a single-channel plan, got {tuple(shape)}!'
+        else:
+            assert len(shape) == trailing + 1 and shape[0] == self.channels, \
+                f'Expected ({self.channels}, ...) for a {self.channels}-channel plan, got {tuple(shape)}!'
 
     def synchronize(self):
         self._lib.sdft_b200_synchronize(self._h)
@@ -109,6 +123,7 @@ class SDFT:
         if _is_torch_cuda(samples):
             import torch
             x = samples.to(torch.float32 if self.td == "f32" else torch.float64).contiguous()
+            self._check_batch(x.shape, 1)
             n = x.shape[-1]
             shape = (n, self._rowlen) if self.channels == 1 else (self.channels, n, self._rowlen)
             fdt = torch.complex64 if self.fd == "f32" else torch.complex128
@@ -116,8 +131,9 @@ class SDFT:
                 out = torch.empty(shape, dtype=fdt, device=x.device)
             else:
                 assert out.is_cuda and out.is_contiguous() and out.dtype == fdt and out.numel() >= n * self._rowlen * self.channels
+                assert out.device == x.device
                 out = out.view(-1)[: n * self._rowlen * self.channels].view(shape)
-            self._use_torch_stream()
+            self._use_torch_stream(x)
             self._f("sdft_batch")(self._h, n, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()))
             self._check()
             return out
@@ -139,10 +155,12 @@ class SDFT:
         if _is_torch_cuda(dfts):
             import torch
             d = dfts.to(torch.complex64 if self.fd == "f32" else torch.complex128).contiguous()
+            assert d.shape[-1] == self._rowlen, f'Expected (samples,frequencies), got {tuple(d.shape)}!'
+            self._check_batch(d.shape, 2)
             n = d.shape[-2]
             shape = (n,) if self.channels == 1 else (self.channels, n)
             y = torch.empty(shape, dtype=torch.float32 if self.td == "f32" else torch.float64, device=d.device)
-            self._use_torch_stream()
+            self._use_torch_stream(d)
             self._f("isdft_batch")(self._h, n, ctypes.c_void_p(d.data_ptr()), ctypes.c_void_p(y.data_ptr()))
             self._check()
             return y
@@ -162,7 +180,8 @@ class SDFT:
         if _is_torch_cuda(samples):
             import torch
             x = samples.to(torch.float32 if self.td == "f32" else torch.float64).contiguous()
-            self._use_torch_stream()
+            self._check_batch(x.shape, 1)
+            self._use_torch_stream(x)
             self._f("advance")(self._h, x.shape[-1], ctypes.c_void_p(x.data_ptr()))
         else:
             x = np.ascontiguousarray(np.atleast_1d(samples), dtype=_NP_TD[self.td])
@@ -190,8 +209,9 @@ class SDFT:
         if _is_torch_cuda(samples):
             import torch
             x = samples.to(torch.float32 if self.td == "f32" else torch.float64).contiguous()
+            self._check_batch(x.shape, 1)
             y = torch.empty_like(x)
-            self._use_torch_stream()
+            self._use_torch_stream(x)
             call(x.shape[-1], ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()))
             return y
         x = np.ascontiguousarray(np.atleast_1d(samples), dtype=_NP_TD[self.td])
@@ -207,7 +227,7 @@ class SDFT:
             d = torch.atleast_2d(x).to(torch.complex64 if self.fd == "f32" else torch.complex128).contiguous()
             assert d.shape[-1] == self.size, f'Expected (samples,frequencies), got {tuple(d.shape)}!'
             out = torch.empty_like(d)
-            self._use_torch_stream()
+            self._use_torch_stream(d)
             self._f("convolve_n")(self._h, d.numel() // self.size // self.channels, ctypes.c_void_p(d.data_ptr()),
                                   ctypes.c_void_p(out.data_ptr()))
             self._check()

@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def seed_of(*parts):
+    """Reproducible RNG seed from the test's parameters (Python's hash() of strings changes per process)."""
+    import zlib
+    return zlib.crc32(repr(parts).encode()) & 0xFFFF
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 import oracle
+from conftest import seed_of
 from oracle import Oracle, Ref
 
 pytestmark = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (reference absent)")
@@ -33,7 +34,7 @@ def test_tables_bit_identical(td, fd, m):
 @pytest.mark.parametrize("window", [0, 1, 2, 3])
 @pytest.mark.parametrize("latency", [1.0, 0.5])
 def test_stream_bit_identical(td, fd, window, latency):
-    rng = np.random.default_rng(hash((td, fd, window)) & 0xFFFF)
+    rng = np.random.default_rng(seed_of(td, fd, window))
     for m in (1, 2, 3, 8, 37, 250):
         o, r = Oracle(td, fd, m, window, latency), Ref(td, fd, m, window, latency)
         for n in (1, 7, 100, 2 * m + 13, 5, 4 * m):
