@@ -341,6 +341,34 @@ def other_configs(torch, SDFT, scratch, peak):
     return res
 
 
+class Watchdog:
+    """The sharded legs run collectives; a rank that dies inside one would leave the others waiting for NCCL's
+    own timeout and the run without its line.  After `seconds` rank 0 prints the line it has (the legs
+    marked as timed out) and every rank leaves."""
+
+    def __init__(self, seconds, json_fd, partial_line):
+        self.fd, self.line = json_fd, partial_line
+        self.lock = threading.Lock()
+        self.done = False
+        self.timer = threading.Timer(seconds, self._bail)
+        self.timer.daemon = True
+        self.timer.start()
+
+    def _bail(self):
+        with self.lock:
+            if self.done:
+                return
+            self.done = True
+            if self.line is not None:
+                os.write(self.fd, (json.dumps(self.line) + "\n").encode())
+        os._exit(0)
+
+    def cancel(self):
+        with self.lock:
+            self.done = True
+        self.timer.cancel()
+
+
 def bind_to_gpu_numa_node(gpu_index):
     """Pins this rank to the CPU cores next to its GPU (NVML's affinity mask), so that the pinned host
     buffers of the e2e legs are first-touched on the NUMA node the GPU's PCIe link hangs off."""
@@ -587,6 +615,33 @@ def run_b200_arm(args, rank, local_rank, world):
                                     "samples in and out, the caller's hop buffer is device memory" % (hop, n_rt, m)}
     del tile
 
+    def make_line(cpu_leg):
+        return {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_analysis / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: 2^20-sample white noise, m=4096, f32 TD / f64 FD, "
+                                   "boxcar+hann+hamming+blackman per step; one channel per GPU",
+                       "n_samples": n, "m": m, "windows": list(WINDOWS), "parallelism": "channel-sharded x%d" % world,
+                       "l2": "no flush: each window writes %.0f GiB (>> 126 MB L2)" % (n * m * 16 / 2 ** 30)},
+            "roofline": roofline, "synthesis": synth, "e2e": e2e, "cpu_baseline": cpu_leg, "clocks": clk,
+            "other_configs": extras,
+            "gpu_launches": int(launches),
+        }
+
+    # ---- the shardings BASELINE.json names: configs[2] by time, configs[3] by channel (every N) --------
+    sharded = {}
+    if not args.no_sharded:
+        import bench_sharded
+        partial = None
+        if rank == 0:
+            partial = dict(make_line(None), sharded_legs={"error": "timed out after %d s" % args.sharded_timeout})
+        guard = Watchdog(args.sharded_timeout, json_fd, partial)
+        sharded = bench_sharded.run_all(torch, dist if world > 1 else None, SDFT, dev, rank, world, reps=3)
+        guard.cancel()
+        launches += int(sum(v.get("gpu_launches_per_shard", 0) + v.get("gpu_launches_per_job", 0)
+                            for v in sharded.values() if isinstance(v, dict)))
+
     # ---- CPU baseline beside it (rank 0, N = 1) -----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -599,18 +654,9 @@ def run_b200_arm(args, rank, local_rank, world):
                "sample": "%d host threads x 4 windows x %d samples, one channel per thread, m=%d" % (threads, spw, m)}
 
     if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t_analysis / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: 2^20-sample white noise, m=4096, f32 TD / f64 FD, "
-                                   "boxcar+hann+hamming+blackman per step; one channel per GPU",
-                       "n_samples": n, "m": m, "windows": list(WINDOWS), "parallelism": "channel-sharded x%d" % world,
-                       "l2": "no flush: each window writes %.0f GiB (>> 126 MB L2)" % (n * m * 16 / 2 ** 30)},
-            "roofline": roofline, "synthesis": synth, "e2e": e2e, "cpu_baseline": cpu, "clocks": clk,
-            "other_configs": extras,
-            "gpu_launches": int(launches),
-        }
+        line = make_line(cpu)
+        line.update(sharded)
+        line["gpu_launches"] = int(launches)
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
@@ -626,6 +672,8 @@ def main():
     ap.add_argument("--e2e-n", type=int, default=1 << 16, help="samples per e2e step (host buffers)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the short measurements of configs 3-5")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the time-/channel-sharded legs (configs 2 and 3)")
+    ap.add_argument("--sharded-timeout", type=int, default=420, help="seconds after which the sharded legs are given up")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

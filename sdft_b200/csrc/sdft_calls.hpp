@@ -420,6 +420,15 @@ bool do_roundtrip(Plan* p, size_t n, const T* in, T* out, const cx<F>* gains = n
     y = (T*)p->synth_out.ptr;
   }
   size_t piece = env_size("SDFT_B200_ROUNDTRIP_PIECE", (size_t)1 << 22);
+  {
+    /* the partial-sum scratch is (channels, groups, piece): wide batches get shorter pieces so that it stays
+     * bounded (1 GiB by default; 512 channels x m = 1024 -> 16 Ki samples per launch, 2e9 bin-updates each) */
+    const size_t cap = env_size("SDFT_B200_ROUNDTRIP_SCRATCH_MB", 1024) << 20;
+    size_t fit = cap / (ch * max_groups * sizeof(F));
+    fit = (fit / 4096) * 4096;
+    if (fit < 4096) fit = 4096;
+    if (piece > fit) piece = fit;
+  }
   if (piece > n) piece = n;
   if (!reserve(p, p->part, ch * max_groups * piece * sizeof(F))) return false;
   for (size_t t0 = 0; t0 < n; t0 += piece)
