@@ -178,6 +178,15 @@ SDFT_B200_API int sdft_b200_get_state(sdft_b200_plan_t* plan, size_t channel, si
 SDFT_B200_API int sdft_b200_set_state(sdft_b200_plan_t* plan, size_t channel, size_t cursor, const void* history,
                                       const void* accumulators);
 
+/* Roofline denominators of THIS board at THIS moment (bench.py): a pure streaming store with the row kernel's own
+ * store instruction and cache policy (kind 0), a pure streaming read with the synthesis kernel's load (kind 1) and
+ * a copy (kind 2, the buffer split in halves) over `bytes` of caller-provided device memory.  Returns GB/s of the
+ * best of `reps` launches, the mean over all of them in *sustained (may be NULL); 0 on failure.  Nothing of the
+ * transform is computed here.  sdft_b200_measure_dfma: DFMA instructions per second (per thread-lane) of a pure
+ * FP64 FMA loop on every SM, the ceiling the fused round trip is quoted against. */
+SDFT_B200_API double sdft_b200_measure_hbm(int kind, void* device_buffer, size_t bytes, int reps, double* sustained);
+SDFT_B200_API double sdft_b200_measure_dfma(int reps);
+
 /* Page-locked host memory so that host-pointer calls can DMA straight into the caller's buffer. */
 SDFT_B200_API void* sdft_b200_host_alloc(size_t bytes);
 SDFT_B200_API void sdft_b200_host_free(void* ptr);

@@ -310,6 +310,82 @@ extern "C" int sdft_b200_set_state(sdft_b200_plan_t* p, size_t channel, size_t c
   return p->status;
 }
 
+/* roofline denominators measured on this board, now: see sdft_peak.cuh.  Everything on a private stream with
+ * CUDA events; `reps` timed launches after 2 warm-up launches; the best launch counts (a burst figure, like
+ * MEASURED_PEAKS.json's copy) and, through *sustained, the mean over all of them. */
+extern "C" double sdft_b200_measure_hbm(int kind, void* device_buffer, size_t bytes, int reps, double* sustained)
+{
+  if (sustained) *sustained = 0.0;
+  if (!device_buffer || bytes < (1u << 20) || reps < 1 || kind < 0 || kind > 2) return 0.0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  double* sink = nullptr;
+  double best = 0.0, total_ms = 0.0;
+  bool ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreate(&e0) == cudaSuccess &&
+            cudaEventCreate(&e1) == cudaSuccess && cudaMalloc(&sink, sizeof(double)) == cudaSuccess;
+  /* a copy splits the buffer into a source half and a destination half */
+  const size_t span = (kind == PEAK_COPY) ? bytes / 2 : bytes;
+  const unsigned long long groups = span / 32;
+  double* dst = (double*)device_buffer;
+  const double* src = (kind == PEAK_COPY) ? (const double*)((char*)device_buffer + groups * 32) : (const double*)device_buffer;
+  const unsigned blocks = 148 * 8;
+  for (int r = -2; ok && r < reps; ++r)
+  {
+    cudaEventRecord(e0, st);
+    if (kind == PEAK_STORE) peak_stream_kernel<PEAK_STORE><<<blocks, 256, 0, st>>>(dst, src, groups, sink);
+    else if (kind == PEAK_READ) peak_stream_kernel<PEAK_READ><<<blocks, 256, 0, st>>>(dst, src, groups, sink);
+    else peak_stream_kernel<PEAK_COPY><<<blocks, 256, 0, st>>>(dst, src, groups, sink);
+    cudaEventRecord(e1, st);
+    ok = cudaEventSynchronize(e1) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+    float ms = 0.f;
+    if (ok && r >= 0 && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess && ms > 0.f)
+    {
+      const double moved = (double)groups * 32.0 * (kind == PEAK_COPY ? 2.0 : 1.0);
+      const double gbps = moved / (ms * 1e-3) / 1e9;
+      if (gbps > best) best = gbps;
+      total_ms += ms;
+      if (sustained) *sustained = moved * (double)(r + 1) / (total_ms * 1e-3) / 1e9;
+    }
+  }
+  if (sink) cudaFree(sink);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (st) cudaStreamDestroy(st);
+  cudaGetLastError();
+  return ok ? best : 0.0;
+}
+
+/* FP64 issue ceiling: DFMA per second of a pure DFMA loop on every SM (sdft_peak.cuh), best of `reps` */
+extern "C" double sdft_b200_measure_dfma(int reps)
+{
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  double* sink = nullptr;
+  double best = 0.0;
+  bool ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreate(&e0) == cudaSuccess &&
+            cudaEventCreate(&e1) == cudaSuccess && cudaMalloc(&sink, sizeof(double)) == cudaSuccess;
+  const unsigned blocks = 148 * 8, iters = 1u << 14;
+  for (int r = -2; ok && r < reps; ++r)
+  {
+    cudaEventRecord(e0, st);
+    peak_dfma_kernel<<<blocks, 256, 0, st>>>(sink, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1, st);
+    ok = cudaEventSynchronize(e1) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+    float ms = 0.f;
+    if (ok && r >= 0 && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess && ms > 0.f)
+    {
+      const double rate = (double)blocks * 256.0 * (double)iters * 8.0 / (ms * 1e-3);
+      if (rate > best) best = rate;
+    }
+  }
+  if (sink) cudaFree(sink);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (st) cudaStreamDestroy(st);
+  cudaGetLastError();
+  return ok ? best : 0.0;
+}
+
 extern "C" void* sdft_b200_host_alloc(size_t bytes)
 {
   void* ptr = nullptr;

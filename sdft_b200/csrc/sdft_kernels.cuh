@@ -37,3 +37,4 @@
 #include "sdft_lane.cuh"
 #include "sdft_scan.cuh"
 #include "sdft_synth.cuh"
+#include "sdft_peak.cuh"
