@@ -321,23 +321,40 @@ def other_configs(torch, SDFT, scratch, peak):
                               "fused_roundtrip_bin_updates_per_s": ch * n * m / t_r}
     # config 5 shape: endless streaming in 4096-sample calls, m = 512, state carried across calls
     m, n, calls = 512, 4096, 1024
-    g = SDFT(m, "hann", 1, td="f32", fd="f64")
-    g._use_torch_stream()
     x = torch.rand(calls * n, device=raw.device) * 2 - 1
     tile = n * m * 16
     xs = [ctypes.c_void_p(x.data_ptr() + c * n * 4) for c in range(calls)]
     os_ = [ctypes.c_void_p(raw.data_ptr() + c * tile) for c in range(calls)]
-    f = g._f("sdft_n")
 
-    def stream_calls():
-        for c in range(calls):
-            f(g._h, n, xs[c], os_[c])
-    t_c = timed(stream_calls, reps=3) / calls
-    g._check()
+    def stream_leg(depth, from_c):
+        g = SDFT(m, "hann", 1, td="f32", fd="f64")
+        g._use_torch_stream()
+        g.set_streaming(depth)
+        f = g._f("sdft_n")
+        hops = g._f("sdft_hops")
+
+        def py_loop():
+            for c in range(calls):
+                f(g._h, n, xs[c], os_[c])
+
+        def c_loop():
+            hops(g._h, calls, n, xs[0], os_[0], n * m)
+        t = timed(c_loop if from_c else py_loop, reps=3) / calls
+        g._check()
+        return t
+    t_serial = stream_leg(1, False)
+    t_serial_c = stream_leg(1, True)
+    t_py = stream_leg(8, False)
+    t_c = stream_leg(8, True)
     res["config5_stream"] = {"workload": "%d back-to-back calls of 4096 samples on one plan, m=512, f64 FD, hann; "
-                                         "rows into %d distinct 32 MiB tiles" % (calls, calls),
+                                         "rows into %d distinct 32 MiB tiles; STREAMING mode "
+                                         "(sdft_b200_set_streaming depth 8: consecutive calls overlap on the GPU), the hop "
+                                         "loop issued from C (sdft_b200_*_sdft_hops = for h: sdft_sdft_n)" % (calls, calls),
                              "us_per_call": t_c * 1e6, "analysis_bin_updates_per_s": n * m / t_c,
-                             "analysis_GBps": n * m * 16 / t_c / 1e9, "analysis_frac_of_hbm_peak": n * m * 16 / t_c / 1e9 / peak}
+                             "analysis_GBps": n * m * 16 / t_c / 1e9, "analysis_frac_of_hbm_peak": n * m * 16 / t_c / 1e9 / peak,
+                             "us_per_call_streaming_python_loop": t_py * 1e6,
+                             "us_per_call_serial_python_loop": t_serial * 1e6, "us_per_call_serial_c_loop": t_serial_c * 1e6,
+                             "hbm_time_per_call_us": n * m * 16 / (peak * 1e9) * 1e6}
     return res
 
 

@@ -96,6 +96,11 @@ typedef struct sdft_b200_plan sdft_b200_plan_t;
   /* extension: analysis state update without writing rows (used to prime a time shard with its         \
    * 2m-sample halo) */                                                                             \
   SDFT_B200_API void sdft_b200_##SFX##_advance(sdft_b200_plan_t* plan, size_t nsamples, const TD* samples);    \
+  /* extension: the hop loop of the reference's drivers (test/test.c:69-83) issued from inside the library:    \
+   * exactly `for h < nhops: sdft_sdft_n(plan, hopsize, samples + h*hopsize, dfts + h*hop_stride)` with       \
+   * hop_stride counted in complex values; saves the caller's per-call overhead when hops are short */         \
+  SDFT_B200_API void sdft_b200_##SFX##_sdft_hops(sdft_b200_plan_t* plan, size_t nhops, size_t hopsize,         \
+                                                 const TD* samples, FDX* dfts, size_t hop_stride);             \
   /* extension, batch plans: samples is (channels, nsamples), dfts is (channels, nsamples, dftsize) */         \
   SDFT_B200_API void sdft_b200_##SFX##_sdft_batch(sdft_b200_plan_t* plan, size_t nsamples, const TD* samples,  \
                                                   FDX* dfts);                                                  \
@@ -136,6 +141,23 @@ SDFT_B200_API int sdft_b200_synchronize(sdft_b200_plan_t* plan);
  * stream).  The plan's own stream is kept for later sdft_b200_set_stream(plan, (void*)-1). */
 SDFT_B200_API int sdft_b200_set_stream(sdft_b200_plan_t* plan, void* cuda_stream);
 
+/* STREAMING MODE for endless sequences of short calls (the hop loop of test/test.c:69-83 with device buffers).
+ * depth <= 1 (default): every call starts after the previous work of the stream has completed -- plain stream
+ * order.  depth D > 1: up to D consecutive *_sdft_n / *_sdft_batch / *_advance calls with DEVICE samples and
+ * DEVICE rows may be in flight at once: a call starts computing while its predecessors still stream their rows
+ * out, and takes the history and the accumulators over through device-side counters instead of a kernel
+ * boundary (a 4096-sample call at dftsize 512 otherwise spends most of its time on start-up and drain
+ * latencies).  Results are bit-identical to the serial mode.  What the caller promises while depth > 1:
+ *   - the samples of a call are complete in device memory when the call is ISSUED (written by work that was
+ *     synchronised with the host or finished before the previous library call was issued), not merely ordered
+ *     before it on the stream;
+ *   - the rows of a call are not overwritten by other work queued between two calls.
+ * What still holds: calls COMPLETE in order, so anything queued behind them in the ordinary way (kernels,
+ * copies, sdft_b200_synchronize, a stream or event wait) sees the rows and the state of all earlier calls.
+ * Costs (depth + 1) copies of the per-channel state (history and accumulators) and `depth` sets of scan scratch.
+ * Not for use from several host threads at once (as everything on one plan). */
+SDFT_B200_API int sdft_b200_set_streaming(sdft_b200_plan_t* plan, unsigned depth);
+
 /* Scan chunk length in samples (multiple of 32, <= 1024); 0 = choose per call from n and m. */
 SDFT_B200_API int sdft_b200_set_chunk(sdft_b200_plan_t* plan, size_t chunk);
 
@@ -148,6 +170,9 @@ SDFT_B200_API int sdft_b200_set_roi(sdft_b200_plan_t* plan, size_t first, size_t
 
 SDFT_B200_API size_t sdft_b200_channels(const sdft_b200_plan_t* plan);
 SDFT_B200_API int sdft_b200_device(const sdft_b200_plan_t* plan);
+/* device bytes of the plan's tables (twiddles, synthesis twiddles, phase source): O(dftsize) for a double
+ * frequency domain, bounded by a fixed budget for float up to dftsize ~ 90 000 */
+SDFT_B200_API size_t sdft_b200_table_bytes(const sdft_b200_plan_t* plan);
 /* number of kernels this plan has launched so far (bench.py reports it as gpu_launches) */
 SDFT_B200_API unsigned long long sdft_b200_launch_count(const sdft_b200_plan_t* plan);
 

@@ -29,6 +29,7 @@ TYPED = {
     "isdft_n": (_V, [_P, _SZ, _P, _P]),
     "isdft_nd": (_V, [_P, _SZ, _P, _P]),
     "advance": (_V, [_P, _SZ, _P]),
+    "sdft_hops": (_V, [_P, _SZ, _SZ, _P, _P, _SZ]),
     "sdft_batch": (_V, [_P, _SZ, _P, _P]),
     "isdft_batch": (_V, [_P, _SZ, _P, _P]),
     "roundtrip_n": (_V, [_P, _SZ, _P, _P]),
@@ -40,10 +41,12 @@ UNTYPED = {
     "sdft_b200_last_error_string": (ctypes.c_char_p, [_P]),
     "sdft_b200_synchronize": (_I, [_P]),
     "sdft_b200_set_stream": (_I, [_P, _P]),
+    "sdft_b200_set_streaming": (_I, [_P, ctypes.c_uint]),
     "sdft_b200_set_chunk": (_I, [_P, _SZ]),
     "sdft_b200_set_roi": (_I, [_P, _SZ, _SZ]),
     "sdft_b200_channels": (_SZ, [_P]),
     "sdft_b200_device": (_I, [_P]),
+    "sdft_b200_table_bytes": (_SZ, [_P]),
     "sdft_b200_launch_count": (ctypes.c_ulonglong, [_P]),
     "sdft_b200_set_profiling": (_I, [_P, _I]),
     "sdft_b200_kernel_ms": (_D, [_P, _I, ctypes.POINTER(ctypes.c_ulonglong)]),

@@ -5,7 +5,7 @@
  *
  * What lives where (reference: struct sdft_plan, c/src/sdft/sdft.h:137-182):
  *   tables   tw_ext[m+4], tws[m], F0[ceil(2m/32)][m+4]         device, written once per plan
- *   state    history[2][2m] and acc_state[2][m+4] (ping-pong) per channel; the cursor lives on the host and the
+ *   state    rings of history[2m] and acc_state[m+4] per channel (two entries, depth + 1 while streaming); the cursor lives on the host and the
  *            modulation phase is a pure function of it (table row + <32 rotations), so it is not stored
  *   scratch  samples, deltas, chunk totals/prefixes/flags of the chained scan, row tiles   device, grow-only
  *
@@ -62,6 +62,13 @@ using namespace sdftb200;
   extern "C" void sdft_b200_##SFX##_sdft_n(sdft_b200_plan_t* p, size_t n, const TD* x, FDX* d)                  \
   {                                                                                                             \
     if (typed<TD, FD>(p, "sdft_sdft_n: plan type mismatch")) do_sdft<TD, FD>(p, n, x, (cx<FD>*)d);              \
+  }                                                                                                             \
+  extern "C" void sdft_b200_##SFX##_sdft_hops(sdft_b200_plan_t* p, size_t nhops, size_t hop, const TD* x,       \
+                                              FDX* d, size_t hop_stride)                                        \
+  {                                                                                                             \
+    if (!typed<TD, FD>(p, "sdft_sdft_hops: plan type mismatch")) return;                                        \
+    for (size_t h = 0; h < nhops; ++h)                                                                          \
+      if (!do_sdft<TD, FD>(p, hop, x + h * hop, (cx<FD>*)d + h * hop_stride)) return;                           \
   }                                                                                                             \
   extern "C" void sdft_b200_##SFX##_sdft_batch(sdft_b200_plan_t* p, size_t n, const TD* x, FDX* d)              \
   {                                                                                                             \
@@ -130,10 +137,10 @@ extern "C" int sdft_b200_synchronize(sdft_b200_plan_t* p)
   DeviceGuard on_device(p->device);
   cudaError_t e = cudaStreamSynchronize(p->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(p->copy_stream);
-  unsigned ctl[2] = { 0, 0 };
-  if (e == cudaSuccess) e = cudaMemcpy(ctl, p->control, sizeof(ctl), cudaMemcpyDeviceToHost);
+  unsigned timed_out = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&timed_out, p->control, sizeof(timed_out), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) plan_fail(p, (int)e, "sdft_b200_synchronize", __FILE__, __LINE__);
-  else if (ctl[1]) plan_fail(p, SDFT_B200_ERR_CHAIN, "chained scan: a carry wait timed out", __FILE__, __LINE__);
+  else if (timed_out) plan_fail(p, SDFT_B200_ERR_CHAIN, "chained scan: a carry wait timed out", __FILE__, __LINE__);
   return p->status;
 }
 
@@ -145,6 +152,20 @@ extern "C" int sdft_b200_set_stream(sdft_b200_plan_t* p, void* cuda_stream)
   DeviceGuard on_device(p->device);
   cudaStreamSynchronize(p->stream);   // work queued on the old stream must not race with the new one
   p->stream = next;
+  return p->status;
+}
+
+extern "C" int sdft_b200_set_streaming(sdft_b200_plan_t* p, unsigned depth)
+{
+  if (!p) return SDFT_B200_ERR_ARG;
+  if (depth < 1) depth = 1;
+  if (depth > 16) depth = 16;
+  if (depth == p->stream_depth) return p->status;
+  DeviceGuard on_device(p->device);
+  if (p->td == kF32 && p->fd == kF32) plan_rings<float, float>(p, depth);
+  else if (p->td == kF32) plan_rings<float, double>(p, depth);
+  else if (p->fd == kF32) plan_rings<double, float>(p, depth);
+  else plan_rings<double, double>(p, depth);
   return p->status;
 }
 
@@ -205,6 +226,7 @@ extern "C" size_t sdft_b200_debug_trace(sdft_b200_plan_t* p, unsigned long long*
 }
 
 extern "C" size_t sdft_b200_channels(const sdft_b200_plan_t* p) { return p ? p->channels : 0; }
+extern "C" size_t sdft_b200_table_bytes(const sdft_b200_plan_t* p) { return p ? p->table_bytes : 0; }
 extern "C" int sdft_b200_device(const sdft_b200_plan_t* p) { return p ? p->device : -1; }
 extern "C" unsigned long long sdft_b200_launch_count(const sdft_b200_plan_t* p) { return p ? p->launches : 0; }
 
@@ -230,11 +252,11 @@ extern "C" int sdft_b200_get_state(sdft_b200_plan_t* p, size_t channel, size_t* 
   cudaError_t e = cudaStreamSynchronize(p->stream);
   if (cursor) *cursor = p->cursor;
   if (e == cudaSuccess && history)
-    e = cudaMemcpy(history, (char*)p->history[p->hist_sel] + channel * 2 * p->m * tbytes, 2 * p->m * tbytes,
+    e = cudaMemcpy(history, (char*)p->history[p->state_sel] + channel * 2 * p->m * tbytes, 2 * p->m * tbytes,
                    cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && accumulators)
   {
-    e = cudaMemcpy(accumulators, (char*)p->acc_state[p->acc_sel] + (channel * p->cells + 2) * cbytes, p->m * cbytes,
+    e = cudaMemcpy(accumulators, (char*)p->acc_state[p->state_sel] + (channel * p->cells + 2) * cbytes, p->m * cbytes,
                    cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && p->prescale != 1.0)
     {
@@ -247,11 +269,11 @@ extern "C" int sdft_b200_get_state(sdft_b200_plan_t* p, size_t channel, size_t* 
   {
     const unsigned threads = 128, blocks = (unsigned)((p->cells + threads - 1) / threads);
     if (p->fd == kF32)
-      phase_at_kernel<float><<<blocks, threads, 0, p->stream>>>((const cx<float>*)p->tw_ext, (const cx<float>*)p->f0,
-                                                                (cx<float>*)p->phase_scratch, (unsigned)p->cells, (unsigned)p->cursor);
+      phase_at_kernel<float><<<blocks, threads, 0, p->stream>>>((const cx<float>*)p->tw_ext, phase_source<float>(p),
+                                                                (cx<float>*)p->phase_scratch, (unsigned)p->cursor);
     else
-      phase_at_kernel<double><<<blocks, threads, 0, p->stream>>>((const cx<double>*)p->tw_ext, (const cx<double>*)p->f0,
-                                                                 (cx<double>*)p->phase_scratch, (unsigned)p->cells, (unsigned)p->cursor);
+      phase_at_kernel<double><<<blocks, threads, 0, p->stream>>>((const cx<double>*)p->tw_ext, phase_source<double>(p),
+                                                                 (cx<double>*)p->phase_scratch, (unsigned)p->cursor);
     p->launches++;
     e = cudaStreamSynchronize(p->stream);
     if (e == cudaSuccess)
@@ -272,7 +294,7 @@ extern "C" int sdft_b200_set_state(sdft_b200_plan_t* p, size_t channel, size_t c
   cudaError_t e = cudaStreamSynchronize(p->stream);
   p->cursor = cursor;          // one cursor per plan: channels of a batch plan advance together
   if (e == cudaSuccess && history)
-    e = cudaMemcpy((char*)p->history[p->hist_sel] + channel * 2 * p->m * tbytes, history, 2 * p->m * tbytes,
+    e = cudaMemcpy((char*)p->history[p->state_sel] + channel * 2 * p->m * tbytes, history, 2 * p->m * tbytes,
                    cudaMemcpyHostToDevice);
   if (e == cudaSuccess && accumulators)
   {
@@ -295,7 +317,7 @@ extern "C" int sdft_b200_set_state(sdft_b200_plan_t* p, size_t channel, size_t c
       cells[2 * c] = bin((size_t)src, 0) * p->prescale;
       cells[2 * c + 1] = bin((size_t)src, 1) * p->prescale * (p->mirrors.conj[q] ? -1.0 : 1.0);
     }
-    char* dst = (char*)p->acc_state[p->acc_sel] + channel * p->cells * cbytes;
+    char* dst = (char*)p->acc_state[p->state_sel] + channel * p->cells * cbytes;
     if (p->fd == kF32)
     {
       std::vector<float> narrow(cells.begin(), cells.end());

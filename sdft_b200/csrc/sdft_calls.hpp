@@ -68,7 +68,9 @@ bool do_sdft(Plan* p, size_t n, const T* samples, cx<F>* dfts)
 
   if (classify(dfts) == kDevice)
   {
-    return analysis_device<T, F>(p, n, x, n, dfts, n * m) && release_samples(p);
+    /* device samples AND device rows: nothing is copied, so a streaming plan may let this call overlap the one
+     * before it (sdft_b200_set_streaming states what the caller promises in return) */
+    return analysis_device<T, F>(p, n, x, n, dfts, n * m, x == samples) && release_samples(p);
   }
 
   /* host destination: compute row tiles on the device and stream them out, overlapping the
@@ -156,7 +158,7 @@ bool do_advance(Plan* p, size_t n, const T* samples)
   const bool host = classify(samples) != kDevice;
   const T* x = stage_samples<T>(p, n, samples, &ok);
   if (!ok) return false;
-  if (!analysis_device<T, F>(p, n, x, n, (cx<F>*)nullptr, 0)) return false;
+  if (!analysis_device<T, F>(p, n, x, n, (cx<F>*)nullptr, 0, !host)) return false;
   if (host) CU_TRY(p, cudaStreamSynchronize(p->stream));
   return true;
 }

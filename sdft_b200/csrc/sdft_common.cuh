@@ -11,7 +11,7 @@ namespace sdftb200
 {
 
 
-constexpr int kF0Stride = 32;     // phase table holds P at every 32nd cursor
+constexpr int kF0Stride = 32;     // finest grid of the float phase table (P at every 32nd cursor) and granularity of chunk lengths
 constexpr int kMaxChunk = 1024;   // longest chunk the kernels accept (samples)
 constexpr int kAutoChunk = 512;   // longest chunk the heuristic picks (measured best on B200)
 

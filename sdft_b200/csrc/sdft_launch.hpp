@@ -64,7 +64,20 @@ bool can_vectorize(const Plan* p, const void* out, size_t out_stride)
   return (row_bins(p) % g == 0) && (p->roi_first % g == 0) && (((uintptr_t)out) % 32 == 0) && (out_stride % g == 0);
 }
 
+unsigned choose_chunk_free(const Plan* p, size_t n, int geo);
+
+/* chunk length of a call: the measured optimum, rounded up to a multiple of the float phase table's stride so
+ * that every chunk but the first of a call starts on a table row (no rotations) */
 unsigned choose_chunk(const Plan* p, size_t n, int geo)
+{
+  unsigned c = choose_chunk_free(p, n, geo);
+  const unsigned s = p->f0_stride;
+  c = ((c + s - 1) / s) * s;
+  if (c > (unsigned)kMaxChunk) c = kMaxChunk;
+  return c;
+}
+
+unsigned choose_chunk_free(const Plan* p, size_t n, int geo)
 {
   if (p->forced_chunk)
   {
@@ -99,9 +112,9 @@ void launch_chain_geo(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps)
   const size_t smem = scan_smem_bytes<F, GEO>(warps, a.sched.chunk) + (size_t)a.stage_rows * Geo<F, GEO>::WC * sizeof(cx<F>);
   constexpr int kDefaultMode = (int)MODE_FAST;
   /* programmatic dependent launch: the CTAs of this call may become resident while the previous kernel
-   * of the stream drains; they wait at the top of the kernel (griddepcontrol.wait) until that kernel
-   * has completed and flushed, so nothing else about the ordering changes.  Hides the launch latency
-   * between back-to-back calls (streaming). */
+   * of the stream drains.  A serial call waits at the top of the kernel (griddepcontrol.wait) until that
+   * kernel has completed and flushed, so nothing else about the ordering changes and only the launch latency
+   * is hidden; a streaming call (ChainArgs::flow) starts computing at once. */
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = p->pdl ? 1 : 0;
@@ -168,7 +181,7 @@ unsigned scan_warps_for(const Plan* p, unsigned chunk, unsigned nchunks, int geo
 /* production path: the single-pass chained scan/emit kernel (deltas and history are its prologue) */
 template <typename T, typename F>
 bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride, F* part = nullptr,
-                      const F* syn_ab = nullptr, bool syn_unit = false)
+                      const F* syn_ab = nullptr, bool syn_unit = false, bool allow_flow = false)
 {
   const unsigned m = (unsigned)p->m;
   const unsigned ch = (unsigned)p->channels;
@@ -186,34 +199,62 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
     return false;
   }
 
-  if (!reserve(p, p->prefix, items * wc * sizeof(cx<F>))) return false;
-  if (!reserve(p, p->chain_totals, items * wc * sizeof(cx<F>))) return false;
-  const size_t flags_before = p->flags.bytes;
-  if (!reserve(p, p->flags, items * sizeof(unsigned))) return false;
-  if (p->flags.bytes != flags_before || p->epoch >= 0x7ffffff0u)
+  /* Streaming (sdft_b200_set_streaming, depth D > 1): a call that produces rows or only updates the state, reads
+   * its samples from device memory and needs little scratch may overlap its predecessors (flow = 1: no wait at
+   * the top of the kernel, hand-over through counters, see sdft_scan.cuh "Between calls").  A serial call waits
+   * for everything before it, so "one serial call, then at most D-1 streaming ones" bounds the calls in flight
+   * to D: the serial call takes scratch slot 0, the streaming ones slots 1 .. D-1, and the state rings have D+1
+   * entries.  Everything else (fused round trips: their finish kernel sits between the scan kernels anyway;
+   * calls with large scratch; the default depth 1) is serial. */
+  const size_t scratch_bytes = 2 * items * wc * sizeof(cx<F>);
+  const bool may_flow = p->stream_depth > 1 && allow_flow && !part && scratch_bytes <= ((size_t)8 << 20);
+  unsigned flow = 0;
+  if (may_flow && p->since_serial + 1 < p->stream_depth)
   {
-    CU_TRY(p, cudaMemsetAsync(p->flags.ptr, 0, p->flags.bytes, p->stream));
-    p->epoch = 0;
+    flow = 1;
+    p->since_serial++;
   }
-  p->epoch++;
+  else
+  {
+    p->since_serial = 0;
+  }
+  const unsigned slot_id = p->since_serial;
+  Plan::Slot& slot = p->slots[slot_id];
+  if (!reserve(p, slot.prefix, items * wc * sizeof(cx<F>))) return false;
+  if (!reserve(p, slot.chain_totals, items * wc * sizeof(cx<F>))) return false;
+  const size_t flags_before = slot.flags.bytes;
+  if (!reserve(p, slot.flags, items * sizeof(unsigned))) return false;
+  if (slot.flags.bytes != flags_before || slot.epoch >= 0x7ffffff0u)
+  {
+    CU_TRY(p, cudaMemsetAsync(slot.flags.ptr, 0, slot.flags.bytes, p->stream));   // a stream operation: serializes
+    slot.epoch = 0;
+  }
+  slot.epoch++;
+  const size_t ring = p->history.size();
 
   ChainArgs<F> a;
   a.sched = sched;
   a.samples = x;
   a.sample_stride = x_stride;
-  a.hist_old = p->history[p->hist_sel];
-  a.hist_new = p->history[p->hist_sel ^ 1];
+  a.hist_old = p->history[p->state_sel];
+  a.hist_new = p->history[(p->state_sel + 1) % ring];
   a.td_double = (type_id<T>::value == kF64) ? 1 : 0;
   a.scale = (F)p->prescale;
   a.tw_ext = (const cx<F>*)p->tw_ext;
-  a.f0 = (const cx<F>*)p->f0;
-  a.acc_in = (const cx<F>*)p->acc_state[p->acc_sel];
-  a.acc_out = (cx<F>*)p->acc_state[p->acc_sel ^ 1];
-  a.prefix = (cx<F>*)p->prefix.ptr;
-  a.totals = (cx<F>*)p->chain_totals.ptr;
-  a.flags = (unsigned*)p->flags.ptr;
-  a.control = p->control;
-  a.epoch = p->epoch;
+  a.phase = phase_source<F>(p);
+  a.acc_in = (const cx<F>*)p->acc_state[p->state_sel];
+  a.acc_out = (cx<F>*)p->acc_state[(p->state_sel + 1) % ring];
+  a.prefix = (cx<F>*)slot.prefix.ptr;
+  a.totals = (cx<F>*)slot.chain_totals.ptr;
+  a.flags = (unsigned*)slot.flags.ptr;
+  a.error = p->control;
+  a.ticket = p->control + 1 + 3 * slot_id;
+  a.sync = p->control + 2 + 3 * slot_id;
+  a.prev_sync = p->control + 2 + 3 * p->prev_slot;
+  a.prev_hist_target = p->slots[p->prev_slot].hist_total;
+  a.prev_acc_target = p->slots[p->prev_slot].acc_total;
+  a.flow = flow;
+  a.epoch = slot.epoch;
   a.total_blocks = (unsigned)items;
   a.nblocks = nblocks;
   a.channels = ch;
@@ -228,12 +269,6 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   a.groups = groups;
   a.stage_rows = (geo == GEO_NARROW) ? scan_stage_rows<F, GEO_NARROW>(warps, chunk) : scan_stage_rows<F, GEO_WIDE>(warps, chunk);
   a.win = make_window_const<F>(p->m, p->window);   // sdft.h:422, :371
-  for (int q = 0; q < 4; ++q)
-  {
-    a.mir_cell[q] = p->mirrors.cell[q];
-    a.mir_src[q] = p->mirrors.src[q] < 0 ? -1 : p->mirrors.src[q] + 2;
-    a.mir_conj[q] = p->mirrors.conj[q];
-  }
   a.trace = nullptr;
 #if defined(SDFT_B200_TRACE)
   if (reserve(p, p->trace, items * 8 * sizeof(unsigned long long)))
@@ -261,19 +296,22 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
     launch_chain<F, EMIT_NONE>(p, a, false, warps, geo);
   }
   CU_TRY(p, cudaGetLastError());
-  p->hist_sel ^= 1;
+  /* what this call will have handed over once its group-0 CTAs / last block items are through */
+  slot.hist_total += nblocks * ch;
+  slot.acc_total += groups * ch;
+  p->prev_slot = slot_id;
+  p->state_sel = (p->state_sel + 1) % ring;
   p->cursor = (size_t)((p->cursor + n) % (2 * (size_t)m));
-  p->acc_sel ^= 1;
   return true;
 }
 
 /* analysis over n samples per channel, everything on the device.
  * x: (channels, x_stride) samples; out: (channels, out_stride) complex rows or nullptr (state only). */
 template <typename T, typename F>
-bool analysis_device(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride)
+bool analysis_device(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride, bool allow_flow = false)
 {
   if (n == 0) return true;
-  return analysis_chained<T, F>(p, n, x, x_stride, out, out_stride);
+  return analysis_chained<T, F>(p, n, x, x_stride, out, out_stride, (F*)nullptr, (const F*)nullptr, false, allow_flow);
 }
 
 template <typename T, typename F>

@@ -49,13 +49,19 @@ struct sdft_b200_plan
   double prescale = 1.0;         // factor folded into the deltas in fast mode (acc_state is scaled by it)
   void* tw_ext = nullptr;
   void* tws = nullptr;
-  void* f0 = nullptr;
+  void* f0 = nullptr;            // float: (f0_rows, cells) phase table at every f0_stride-th cursor; double: the P[0] row only
   size_t f0_rows = 0;
+  unsigned f0_stride = 32;
+  void* roots = nullptr;         // double: the 2m roots of unity E[j] = exp(-2 pi i j / 2m) (PhaseSource)
+  size_t table_bytes = 0;        // device bytes of tw_ext + tws + f0 + roots
 
-  void* history[2] = { nullptr, nullptr };
-  int hist_sel = 0;
-  void* acc_state[2] = { nullptr, nullptr };     // ping-pong, same reason (neighbouring groups share halo cells)
-  int acc_sel = 0;
+  /* State rings: call e reads entry state_sel and writes entry (state_sel + 1) % size.  Two entries (ping-pong:
+   * neighbouring groups share halo cells, and a call reads the old history while it writes the new one) for
+   * serial calls; stream_depth + 1 entries while streaming, so that no call in flight writes an entry another
+   * call in flight still reads (sdft_launch.hpp: streaming) */
+  std::vector<void*> history;      // (channels, 2m) time-domain samples each
+  std::vector<void*> acc_state;    // (channels, cells) complex each
+  size_t state_sel = 0;
   void* phase_scratch = nullptr;   // cells complex values, introspection only
 
   Buffer samples, synth_out, tile[2], part, weights;
@@ -66,9 +72,21 @@ struct sdft_b200_plan
   void* stage[2] = { nullptr, nullptr };   // pinned host staging for PAGEABLE caller buffers (grow-only)
   size_t stage_bytes[2] = { 0, 0 };
   cudaEvent_t stage_done[2] = { nullptr, nullptr };
-  Buffer prefix, chain_totals, flags;   // chained scan: inclusive prefixes, chunk totals, epoch-stamped flags
-  unsigned* control = nullptr;   // [0] work ticket, [1] spin-wait timeout flag
-  unsigned epoch = 0;
+  /* Scratch of the chained scan, one slot per call that may be in flight: inclusive prefixes, block totals,
+   * epoch-stamped flags; on the device (control): [0] spin-wait timeout flag of the plan, then per slot a work
+   * ticket and the two hand-over counters (history pieces / accumulator rows written), whose running totals the
+   * host keeps so that the next call knows what to wait for */
+  struct Slot
+  {
+    Buffer prefix, chain_totals, flags;
+    unsigned epoch = 0;
+    unsigned hist_total = 0, acc_total = 0;
+  };
+  std::vector<Slot> slots;
+  unsigned* control = nullptr;
+  unsigned stream_depth = 1;     // calls that may be in flight at once (1: serial; sdft_b200_set_streaming)
+  unsigned since_serial = 0;     // streaming calls issued since the last serial one
+  unsigned prev_slot = 0;        // slot of the previous call
 
   /* optional CUDA-event timing of the dominant kernels (bench.py roofline): [0] analysis emit, [1] synthesis */
   bool profiling = false;
@@ -211,11 +229,80 @@ bool reserve_stage(Plan* p, int b, size_t bytes)
 
 template <typename F> size_t csize() { return sizeof(cx<F>); }
 
+/* Cursors per row of the float phase table: 32 while the table fits the budget, doubling with m beyond that
+ * (up to the longest chunk, 1024), so that the table grows like m^2 / stride only until the budget and stays
+ * O(m) per row.  m = 65536: stride 512, 256 rows, 128 MiB.  Past stride 1024 the table itself has to grow; sizes
+ * whose table would not fit a quarter of the device are rejected up front (plan_create) with a clear message
+ * instead of a cudaMalloc failure deep inside.  SDFT_B200_F0_BUDGET_MB overrides the budget (tests). */
+inline unsigned f0_stride_for(size_t m, size_t entry_bytes, size_t budget)
+{
+  unsigned stride = kF0Stride;
+  while (stride < (unsigned)kMaxChunk && ((2 * m + stride - 1) / stride) * (m + 4) * entry_bytes > budget) stride *= 2;
+  return stride;
+}
+
+template <typename F> PhaseSource<F> phase_source(const sdft_b200_plan* p)
+{
+  PhaseSource<F> s;
+  s.f0 = (const cx<F>*)p->f0;
+  s.roots = (const cx<F>*)p->roots;
+  s.cells = (unsigned)p->cells;
+  s.m = (unsigned)p->m;
+  s.period = (unsigned)(2 * p->m);
+  s.stride = p->f0_stride;
+  for (int q = 0; q < 4; ++q)
+  {
+    s.mir_cell[q] = p->mirrors.cell[q];
+    s.mir_src[q] = p->mirrors.src[q] < 0 ? -1 : p->mirrors.src[q] + 2;
+    s.mir_conj[q] = p->mirrors.conj[q];
+  }
+  return s;
+}
+
 /* -------- plan construction -------- */
+/* (re)allocates the state rings and scratch slots for `depth` calls in flight, carrying the current state over */
+template <typename T, typename F>
+bool plan_rings(Plan* p, unsigned depth)
+{
+  const size_t m = p->m, cells = p->cells, ch = p->channels;
+  const size_t hbytes = ch * 2 * m * sizeof(T), abytes = ch * cells * sizeof(cx<F>);
+  if (p->stream) CU_TRY(p, cudaStreamSynchronize(p->stream));
+  std::vector<void*> hist(depth + 1, nullptr), acc(depth + 1, nullptr);
+  for (unsigned i = 0; i <= depth; ++i)
+  {
+    CU_TRY(p, cudaMalloc(&hist[i], hbytes));
+    CU_TRY(p, cudaMalloc(&acc[i], abytes));
+    CU_TRY(p, cudaMemset(hist[i], 0, hbytes));
+    CU_TRY(p, cudaMemset(acc[i], 0, abytes));
+  }
+  if (!p->history.empty())
+  {
+    CU_TRY(p, cudaMemcpy(hist[0], p->history[p->state_sel], hbytes, cudaMemcpyDeviceToDevice));
+    CU_TRY(p, cudaMemcpy(acc[0], p->acc_state[p->state_sel], abytes, cudaMemcpyDeviceToDevice));
+    for (void* q : p->history) cudaFree(q);
+    for (void* q : p->acc_state) cudaFree(q);
+  }
+  p->history.swap(hist);
+  p->acc_state.swap(acc);
+  p->state_sel = 0;
+  for (Plan::Slot& s : p->slots)
+    for (Buffer* b : { &s.prefix, &s.chain_totals, &s.flags })
+      if (b->ptr) cudaFree(b->ptr);
+  p->slots.assign(depth, Plan::Slot());
+  if (p->control) cudaFree(p->control);
+  p->control = nullptr;
+  CU_TRY(p, cudaMalloc(&p->control, (1 + 3 * (size_t)depth) * sizeof(unsigned)));
+  CU_TRY(p, cudaMemset(p->control, 0, (1 + 3 * (size_t)depth) * sizeof(unsigned)));
+  p->stream_depth = depth;
+  p->since_serial = 0;
+  p->prev_slot = 0;
+  return true;
+}
+
 template <typename T, typename F>
 bool plan_build(Plan* p)
 {
-  const size_t m = p->m, cells = p->cells, ch = p->channels;
+  const size_t m = p->m, cells = p->cells;
   std::vector<cx<F>> tw, tws;
   make_tables<F>(m, p->latency, tw, tws);
 
@@ -241,27 +328,64 @@ bool plan_build(Plan* p)
     }
   }
 
-  p->f0_rows = (2 * m + kF0Stride - 1) / kF0Stride;
+  const bool table = (type_id<F>::value == kF32);      // float: recurrence table; double: roots of unity (PhaseSource)
+  if (table)
+  {
+    const size_t budget = env_size("SDFT_B200_F0_BUDGET_MB", 192) << 20;
+    p->f0_stride = f0_stride_for(m, sizeof(cx<F>), budget);
+    p->f0_rows = (2 * m + p->f0_stride - 1) / p->f0_stride;
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(p, cudaMemGetInfo(&free_b, &total_b));
+    if (p->f0_rows * cells * sizeof(cx<F>) > free_b / 4)
+    {
+      plan_fail(p, SDFT_B200_ERR_ARG, "sdft_alloc: dftsize too large for the float phase table on this device "
+                                      "(float frequency domain needs the reference's sequential recurrence: "
+                                      "m^2/64 bytes once the table stride has reached the longest chunk)", __FILE__, __LINE__);
+      return false;
+    }
+  }
+  else
+  {
+    p->f0_stride = kF0Stride;
+    p->f0_rows = 1;
+  }
   CU_TRY(p, cudaMalloc(&p->tw_ext, cells * sizeof(cx<F>)));
   CU_TRY(p, cudaMalloc(&p->tws, m * sizeof(cx<F>)));
   CU_TRY(p, cudaMalloc(&p->f0, p->f0_rows * cells * sizeof(cx<F>)));
-  CU_TRY(p, cudaMalloc(&p->history[0], ch * 2 * m * sizeof(T)));
-  CU_TRY(p, cudaMalloc(&p->history[1], ch * 2 * m * sizeof(T)));
-  CU_TRY(p, cudaMalloc(&p->acc_state[0], ch * cells * sizeof(cx<F>)));
-  CU_TRY(p, cudaMalloc(&p->acc_state[1], ch * cells * sizeof(cx<F>)));
-  CU_TRY(p, cudaMalloc(&p->control, 2 * sizeof(unsigned)));
-  CU_TRY(p, cudaMemsetAsync(p->control, 0, 2 * sizeof(unsigned), p->stream));
+  p->table_bytes = (cells + m + p->f0_rows * cells) * sizeof(cx<F>);
+  if (!table)
+  {
+    /* E[j] = exp(-2 pi i j / 2m), evaluated in long double and rounded once */
+    std::vector<cx<F>> roots(2 * m);
+    const long double step = -2.0L * acosl(-1.0L) / (long double)(2 * m);
+    for (size_t j = 0; j < 2 * m; ++j)
+    {
+      roots[j].r = (F)cosl(step * (long double)j);
+      roots[j].i = (F)sinl(step * (long double)j);
+    }
+    CU_TRY(p, cudaMalloc(&p->roots, 2 * m * sizeof(cx<F>)));
+    CU_TRY(p, cudaMemcpy(p->roots, roots.data(), 2 * m * sizeof(cx<F>), cudaMemcpyHostToDevice));
+    p->table_bytes += 2 * m * sizeof(cx<F>);
+  }
+  if (!plan_rings<T, F>(p, 1)) return false;
   CU_TRY(p, cudaMalloc(&p->phase_scratch, cells * sizeof(cx<F>)));
 
   CU_TRY(p, cudaMemcpyAsync(p->tw_ext, tw_ext.data(), cells * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
   CU_TRY(p, cudaMemcpyAsync(p->tws, tws.data(), m * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
   /* stage P0 (1, or 0 for always-zero mirror cells), expand it into the table */
   CU_TRY(p, cudaMemcpyAsync(p->phase_scratch, p0.data(), cells * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
-  const unsigned threads = 128;
-  phase_table_kernel<F><<<(unsigned)((cells + threads - 1) / threads), threads, 0, p->stream>>>(
-      (const cx<F>*)p->tw_ext, (const cx<F>*)p->phase_scratch, (cx<F>*)p->f0, (unsigned)cells, (unsigned)(2 * m));
-  p->launches++;
-  CU_TRY(p, cudaGetLastError());
+  if (table)
+  {
+    const unsigned threads = 128;
+    phase_table_kernel<F><<<(unsigned)((cells + threads - 1) / threads), threads, 0, p->stream>>>(
+        (const cx<F>*)p->tw_ext, (const cx<F>*)p->phase_scratch, (cx<F>*)p->f0, (unsigned)cells, (unsigned)(2 * m), p->f0_stride);
+    p->launches++;
+    CU_TRY(p, cudaGetLastError());
+  }
+  else
+  {
+    CU_TRY(p, cudaMemcpyAsync(p->f0, p0.data(), cells * sizeof(cx<F>), cudaMemcpyHostToDevice, p->stream));
+  }
   CU_TRY(p, cudaStreamSynchronize(p->stream));   // host vectors go out of scope
   return true;
 }
@@ -271,11 +395,10 @@ bool plan_reset(Plan* p)
 {
   const size_t m = p->m, cells = p->cells, ch = p->channels;
   p->cursor = 0;
-  p->hist_sel = 0;
-  p->acc_sel = 0;
+  /* stream-ordered: the memsets run after every call queued so far has completed (calls complete in order) */
+  p->state_sel = 0;
   CU_TRY(p, cudaMemsetAsync(p->history[0], 0, ch * 2 * m * sizeof(T), p->stream));
-  CU_TRY(p, cudaMemsetAsync(p->acc_state[0], 0, ch * cells * sizeof(cx<F>), p->stream));
-  CU_TRY(p, cudaMemsetAsync(p->acc_state[1], 0, ch * cells * sizeof(cx<F>), p->stream));
+  for (void* a : p->acc_state) CU_TRY(p, cudaMemsetAsync(a, 0, ch * cells * sizeof(cx<F>), p->stream));
   return true;
 }
 
@@ -285,8 +408,12 @@ void plan_destroy(Plan* p)
   DeviceGuard on_device(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
-  void* ptrs[] = { p->tw_ext, p->tws, p->f0, p->history[0], p->history[1], p->acc_state[0], p->acc_state[1], p->phase_scratch,
-                   p->prefix.ptr, p->chain_totals.ptr, p->flags.ptr, p->control,
+  for (void* q : p->history) cudaFree(q);
+  for (void* q : p->acc_state) cudaFree(q);
+  for (Plan::Slot& s : p->slots)
+    for (Buffer* b : { &s.prefix, &s.chain_totals, &s.flags })
+      if (b->ptr) cudaFree(b->ptr);
+  void* ptrs[] = { p->tw_ext, p->tws, p->f0, p->roots, p->phase_scratch, p->control,
                    p->samples.ptr, p->synth_out.ptr, p->part.ptr, p->weights.ptr, p->syn_ab.ptr, p->trace.ptr, p->tile[0].ptr, p->tile[1].ptr };
   for (void* q : ptrs)
     if (q) cudaFree(q);

@@ -40,6 +40,23 @@ namespace sdftb200
  *      flag clearing between calls); consumers acquire the flag and read the cells through L2.  A wait
  *      that exceeds kSpinLimitNs sets *error and gives up, so a logic error shows up as a reported
  *      failure, not as a hung device.
+ *
+ *      Between calls.  A call hands three things to the next call on the plan: the 2m-sample history
+ *      (written by the CTAs of group 0 in their prologue), the accumulators (written by the last block item
+ *      of every chain) and, implicitly, the order of completion.  Each hand-over has its own counter
+ *      (ChainArgs::sync: [0] history pieces written, [1] accumulator rows written; monotonic, the host knows
+ *      the totals), so the consumer can wait for exactly what it needs:
+ *        - serial call (flow == 0, the default): griddepcontrol.wait at the top -- the previous kernel has
+ *          completed and flushed, every counter is trivially there, nothing is polled;
+ *        - STREAMING call (flow == 1, sdft_b200_set_streaming): no wait at the top.  The kernel is launched
+ *          with programmatic stream serialization, so its CTAs become resident as soon as every CTA of the
+ *          previous call has started, compute their deltas and chunk totals while that call is still
+ *          streaming rows out, and poll the counters only where the data is needed: the history before the
+ *          deltas of the first 2m samples, the accumulators at the head of each chain.  Scratch (ticket,
+ *          flags, totals, prefixes) and state buffers rotate through rings sized by the streaming depth, and
+ *          every depth-th call is a serial one, which bounds the calls in flight (sdft_launch.hpp).
+ *      Every thread ends with griddepcontrol.wait: a call completes only after its predecessor has, so work
+ *      queued behind the calls in the ordinary way still sees all of them finished.
  * ---------------------------------------------------------------------------------------------- */
 #ifndef SDFT_B200_EMIT_UNROLL
 #define SDFT_B200_EMIT_UNROLL 2        // time steps unrolled in the row loop
@@ -61,13 +78,19 @@ template <typename F> struct ChainArgs
   int td_double;           // time-domain type of samples/history: 0 float, 1 double
   F scale;                 // factor folded into the deltas (exactly 1 unless double MODE_FAST folds the window weight)
   const cx<F>* tw_ext;     // (cells)
-  const cx<F>* f0;         // (rows, cells)
+  PhaseSource<F> phase;    // where chunk-start phases come from (sdft_schedule.cuh); also carries the mirror-cell map
   const cx<F>* acc_in;     // (channels, cells)
   cx<F>* acc_out;
   cx<F>* totals;           // (channels, nblocks, groups, WC) aggregate of each block item
   cx<F>* prefix;           // (channels, nblocks, groups, WC) inclusive prefix after each block item
   unsigned* flags;         // (channels, nblocks, groups): 2*epoch = aggregate published, 2*epoch+1 = prefix published
-  unsigned* control;       // [0] ticket counter, [1] error flag
+  unsigned* ticket;        // work ticket of this call's scratch slot (rearmed by the last ticket of the launch)
+  unsigned* error;         // spin-wait timeout flag of the plan
+  unsigned* sync;          // this call's hand-over counters: [0] history pieces written, [1] accumulator rows written
+  const unsigned* prev_sync;   // the previous call's counters ...
+  unsigned prev_hist_target;   // ... and the values they reach once that call has handed over history / accumulators
+  unsigned prev_acc_target;
+  unsigned flow;           // 1: streaming call, may overlap the previous call (see the header comment); 0: serial
   unsigned epoch;
   unsigned total_blocks;   // nblocks * channels * groups
   unsigned nblocks;        // block items per chain: ceil(nchunks / warps per CTA)
@@ -83,9 +106,6 @@ template <typename F> struct ChainArgs
   unsigned groups;
   unsigned stage_rows;     // rows of look-back staging in shared memory (scan_stage_rows)
   WindowConst<F> win;
-  int mir_cell[4];         // the four mirror cells (sdft.h:589-595) ...
-  int mir_src[4];          // ... the CELL each one copies (-1: always zero) ...
-  int mir_conj[4];         // ... and whether the copy is conjugated; read by the halo-free kernels only
   unsigned long long* trace;   // -DSDFT_B200_TRACE builds only: 8 %globaltimer stamps per CTA, else unused
 };
 
@@ -131,6 +151,34 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
+}
+/* completion order: a thread that has passed this has seen the previous kernel of the stream complete (a no-op
+ * for the second time and for kernels launched without programmatic serialization) */
+__device__ __forceinline__ void grid_dependency_wait()
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v)
+{
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+constexpr unsigned long long kSpinLimitNsFwd = 20ull * 1000ull * 1000ull * 1000ull;
+/* one thread: wait until the monotonic counter has reached `target` (wrap-safe), acquire what its writers released */
+__device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target, unsigned* error)
+{
+  unsigned spins = 0;
+  unsigned long long t_start = 0;
+  while ((int)(ld_acquire_u32(ctr) - target) < 0)
+  {
+    if (++spins < 64u) continue;
+    __nanosleep(100);
+    if (t_start == 0) t_start = global_timer_ns();
+    else if (global_timer_ns() - t_start > kSpinLimitNsFwd)
+    {
+      atomicExch(error, 1u);
+      break;
+    }
+  }
 }
 template <typename F> __device__ __forceinline__ cx<F> load_l2(const cx<F>* p);
 template <> __device__ __forceinline__ cx<double> load_l2<double>(const cx<double>* p)
@@ -191,7 +239,8 @@ __device__ __forceinline__ void chunk_deltas(const ChainArgs<F>& a, unsigned ch,
   {
     const unsigned long long t = cs.t0 + i;
     const T newest = x[t];
-    const T oldest = (t < period) ? ho[t] : x[t - period];
+    const T oldest = (t < period) ? __ldcg(ho + t) : x[t - period];     // history through L2: a streaming call reads
+                                                                       // what another kernel wrote a moment ago
     const T diff = newest - oldest;
     sdelta[i] = (F)diff * a.scale;
   }
@@ -207,7 +256,7 @@ __device__ __forceinline__ void roll_history(const ChainArgs<F>& a, unsigned ch,
   for (unsigned i = jb * blockDim.x + threadIdx.x; i < period; i += a.nblocks * blockDim.x)
   {
     const unsigned long long pos = a.sched.n + i;   // position inside history || samples
-    hn[i] = (pos < period) ? ho[pos] : x[pos - period];
+    hn[i] = (pos < period) ? __ldcg(ho + pos) : x[pos - period];
   }
 }
 
@@ -226,6 +275,26 @@ __device__ __forceinline__ void cp_async_wait_all()
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+/* the plan's accumulators at the start of this call (one warp, this lane's cells e0 .. e0+CPL-1).  A streaming
+ * call may get here while the previous call is still adding up: wait for its accumulator rows first. */
+template <typename F, int CPL>
+__device__ __forceinline__ void load_plan_acc(const ChainArgs<F>& a, unsigned ch, int e0, unsigned lane, cx<F>* acc)
+{
+  if (a.flow)
+  {
+    if (lane == 0) wait_counter(a.prev_sync + 1, a.prev_acc_target, a.error);
+    __syncwarp();
+  }
+  const cx<F>* ai = a.acc_in + (size_t)ch * a.cells;
+#pragma unroll
+  for (int b = 0; b < CPL; ++b)
+  {
+    const int e = e0 + b;
+    if (e >= 0 && e < (int)a.cells) acc[b] = load_l2<F>(ai + e);
+    else { acc[b].r = (F)0; acc[b].i = (F)0; }
+  }
+}
+
 /* carry at the first chunk of block item `jb` (jb > 0): decoupled look-back over the preceding block
  * items of the chain, deterministic left-to-right summation (one warp; see the header comment).
  * The walk stops at the nearest item `q` with a published inclusive prefix -- or at item 0, whose
@@ -235,8 +304,7 @@ __device__ __forceinline__ void cp_async_wait_all()
  * trip for up to stage_rows rows instead of one per four -- and then added in order. */
 template <typename F, int GEO>
 __device__ __forceinline__ void look_back(const ChainArgs<F>& a, size_t item, size_t item_stride, unsigned jb, unsigned lane,
-                                          const cx<F>* acc_in_cells, cx<F>* stage, unsigned stage_rows, cx<F>* acc,
-                                          unsigned trace_slot)
+                                          unsigned ch, int e0, cx<F>* stage, unsigned stage_rows, cx<F>* acc, unsigned trace_slot)
 {
   typedef Geo<F, GEO> G;
   typedef Arith<F> A;
@@ -284,7 +352,7 @@ __device__ __forceinline__ void look_back(const ChainArgs<F>& a, size_t item, si
     if (t_start == 0) t_start = global_timer_ns();
     else if (global_timer_ns() - t_start > kSpinLimitNs)
     {
-      if (lane == 0) atomicExch(&a.control[1], 1u);
+      if (lane == 0) atomicExch(a.error, 1u);
       q = 0;
       from_start = true;
       break;
@@ -299,8 +367,7 @@ __device__ __forceinline__ void look_back(const ChainArgs<F>& a, size_t item, si
   const size_t rstride = item_stride * G::WC;
   if (from_start)
   {
-#pragma unroll
-    for (int b = 0; b < G::CPL; ++b) acc[b] = acc_in_cells[b];
+    load_plan_acc<F, G::CPL>(a, ch, e0, lane, acc);
   }
   else
   {
@@ -372,13 +439,25 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   /* programmatic dependent launch (see launch_chain): nothing of the previous kernel in the stream may be
    * read or overwritten before it has completed; dependents of THIS kernel may start filling SMs as
    * soon as every CTA of it has got this far */
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (!a.flow) grid_dependency_wait();
   asm volatile("griddepcontrol.launch_dependents;");
   if (threadIdx.x == 0)
   {
-    const unsigned t = atomicAdd(&a.control[0], 1u);
-    if (t == a.total_blocks - 1) a.control[0] = 0;   // last ticket of the launch: rearm for the next call
+    const unsigned t = atomicAdd(a.ticket, 1u);
+    if (t == a.total_blocks - 1) *a.ticket = 0;   // last ticket of the launch: rearm the slot for its next call
     s_ticket = t;
+    if (a.flow)
+    {
+      /* streaming: the previous call may still be writing the history this CTA reads -- for the deltas of
+       * the call's first 2m samples (its first chunk is the earliest) or for rolling a short call's history */
+      const unsigned per = a.channels * a.groups;
+      const unsigned jb0 = t / per;
+      const unsigned g0 = (t - jb0 * per) % a.groups;
+      const unsigned first = jb0 * (blockDim.x >> 5);
+      const bool reads_hist = (first < a.sched.nchunks && chunk_span(a.sched, first).t0 < a.sched.period) ||
+                              (g0 == 0 && a.sched.n < a.sched.period);
+      if (reads_hist) wait_counter(a.prev_sync, a.prev_hist_target, a.error);
+    }
   }
   __syncthreads();
   const unsigned ticket = s_ticket;
@@ -409,6 +488,9 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   {
     if (a.td_double) roll_history<double, F>(a, ch, jb);
     else roll_history<float, F>(a, ch, jb);
+    /* hand-over: this CTA's piece of the next call's history is written */
+    __syncthreads();
+    if (threadIdx.x == 0) red_release_add_u32(a.sync, 1u);
   }
   __syncwarp();
   SDFT_B200_STAMP(1);   // deltas in shared memory
@@ -439,10 +521,10 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
       /* total = P_start * sum_i tw^i delta_i, the inner sum by Horner from the chunk's last sample,
        * four samples per step once the remaining count is a multiple of four */
       typedef FastOps<F, MODE> X;
-      /* the table row of the starting phase is fetched now so that its latency hides under the sum */
+      /* the starting phase is fetched now (one root of unity per cell) so that its latency hides under the sum */
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b)
-        L.ph[b] = live[b] ? a.f0[(size_t)(cs.cursor0 / kF0Stride) * a.cells + (e0 + b)] : zero;
+        L.ph[b] = live[b] ? phase_at<F>(a.phase, e0 + b, cs.cursor0, L.tw[b]) : zero;
       int i = (int)cs.len;
       for (int r = i & 3; r > 0; --r)
       {
@@ -467,9 +549,6 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
           for (int b = 0; b < G::CPL; ++b) tot[b] = X::horner4(tot[b], L.tw[b], w2[b], w3[b], w4[b], d0, d1, d2, d3);
         }
       }
-      for (unsigned r = cs.cursor0 % kF0Stride; r > 0; --r)     // only the first chunk of a call starts off the table grid
-#pragma unroll
-        for (int b = 0; b < G::CPL; ++b) L.ph[b] = A::rotate(L.ph[b], L.tw[b]);
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b) tot[b] = X::cmul(L.ph[b], tot[b]);
     }
@@ -487,7 +566,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
       {
         h[b].r = 0.0; h[b].i = 0.0;
         w[b].r = (double)L.tw[b].r; w[b].i = (double)L.tw[b].i;
-        L.ph[b] = live[b] ? phase_at<F>(a.f0, a.cells, e0 + b, cs.cursor0, L.tw[b]) : zero;
+        L.ph[b] = live[b] ? phase_at<F>(a.phase, e0 + b, cs.cursor0, L.tw[b]) : zero;
       }
 #pragma unroll 2
       for (int i = (int)cs.len - 1; i >= 0; --i)
@@ -508,7 +587,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
     {
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b)
-        L.ph[b] = live[b] ? phase_at<F>(a.f0, a.cells, e0 + b, cs.cursor0, L.tw[b]) : zero;
+        L.ph[b] = live[b] ? phase_at<F>(a.phase, e0 + b, cs.cursor0, L.tw[b]) : zero;
       const unsigned body = cs.len - 1;
 #pragma unroll 2
       for (unsigned i = 0; i < body; ++i)
@@ -558,18 +637,8 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
     }
     SDFT_B200_STAMP(3);   // aggregate published
     cx<F> carry[G::CPL];
-    {
-      const cx<F>* ai = a.acc_in + (size_t)ch * a.cells;
-#pragma unroll
-      for (int b = 0; b < G::CPL; ++b) carry[b] = live[b] ? ai[e0 + b] : zero;
-    }
-    if (jb > 0)
-    {
-      cx<F> start[G::CPL];
-#pragma unroll
-      for (int b = 0; b < G::CPL; ++b) start[b] = carry[b];
-      look_back<F, GEO>(a, item, item_stride, jb, lane, start, sstage, a.stage_rows, carry, ticket);
-    }
+    if (jb > 0) look_back<F, GEO>(a, item, item_stride, jb, lane, ch, e0, sstage, a.stage_rows, carry, ticket);
+    else load_plan_acc<F, G::CPL>(a, ch, e0, lane, carry);
     SDFT_B200_STAMP(4);   // carry known
 #pragma unroll
     for (int b = 0; b < G::CPL; ++b) agg[b] = A::cadd(carry[b], agg[b]);
@@ -599,11 +668,11 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
           ao[e] = agg[b];
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            if (a.mir_src[q] == e)
+            if (a.phase.mir_src[q] == e)
             {
               cx<F> v = agg[b];
-              if (a.mir_conj[q]) v.i = -v.i;
-              ao[a.mir_cell[q]] = v;
+              if (a.phase.mir_conj[q]) v.i = -v.i;
+              ao[a.phase.mir_cell[q]] = v;
             }
         }
       }
@@ -613,6 +682,9 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
         for (int b = 0; b < G::CPL; ++b)
           if (live[b]) ao[e0 + b] = agg[b];
       }
+      /* hand-over: this chain's accumulators are in place for the next call */
+      __syncwarp();
+      if (lane == 0) red_release_add_u32(a.sync + 1, 1u);
     }
 #pragma unroll
     for (int b = 0; b < G::CPL; ++b) L.acc[b] = carry[b];
@@ -635,13 +707,13 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
     }
   }
   SDFT_B200_STAMP(5);   // carries distributed, replay starts
-  if (!valid) return;
+  if (!valid) { grid_dependency_wait(); return; }
 
   /* ---- phase C: replay from the carry and stream the rows out ---- */
   if (EMIT == EMIT_ROWS)
   {
     /* groups without a bin inside the region of interest have done their share (the carries): no rows */
-    if (group * (unsigned)G::SPAN >= roi_end || (group + 1u) * (unsigned)G::SPAN <= roi_first) return;
+    if (group * (unsigned)G::SPAN >= roi_end || (group + 1u) * (unsigned)G::SPAN <= roi_first) { grid_dependency_wait(); return; }
     const size_t row_stride = a.roi_count;
     L.dst = a.out + (size_t)ch * a.out_channel_stride + (size_t)cs.t0 * row_stride + ((long long)e0 - 2 - (long long)roi_first);
     if constexpr (SLIDE)
@@ -680,7 +752,7 @@ SDFT_B200_PRAGMA_UNROLL(SDFT_B200_EMIT_UNROLL)
       /* the starting phase is generated again rather than kept in registers across phase A */
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b)
-        L.ph[b] = live[b] ? phase_at<F>(a.f0, a.cells, e0 + b, cs.cursor0, L.tw[b]) : zero;
+        L.ph[b] = live[b] ? phase_at<F>(a.phase, e0 + b, cs.cursor0, L.tw[b]) : zero;
       const unsigned body = cs.wraps ? cs.len - 1 : cs.len;
 SDFT_B200_PRAGMA_UNROLL(SDFT_B200_EMIT_UNROLL)
       for (unsigned i = 0; i < body; ++i)
@@ -691,7 +763,7 @@ SDFT_B200_PRAGMA_UNROLL(SDFT_B200_EMIT_UNROLL)
       {
         cx<F> restart[G::CPL];
 #pragma unroll
-        for (int b = 0; b < G::CPL; ++b) restart[b] = live[b] ? a.f0[e0 + b] : zero;
+        for (int b = 0; b < G::CPL; ++b) restart[b] = live[b] ? phase_restart<F>(a.phase, e0 + b) : zero;
         L.template step<true, FUSED>(sdelta[body], restart, a.win, row_stride);
       }
     }
@@ -723,8 +795,8 @@ SDFT_B200_PRAGMA_UNROLL(SDFT_B200_EMIT_UNROLL)
 #pragma unroll
       for (int b = 0; b < G::CPL; ++b)
       {
-        L.ph[b] = live[b] ? phase_at<F>(a.f0, a.cells, e0 + b, cs.cursor0, L.tw[b]) : zero;
-        restart[b] = live[b] ? a.f0[e0 + b] : zero;
+        L.ph[b] = live[b] ? phase_at<F>(a.phase, e0 + b, cs.cursor0, L.tw[b]) : zero;
+        restart[b] = live[b] ? phase_restart<F>(a.phase, e0 + b) : zero;
       }
     }
     /* eight steps per reduction while they last, then single steps; no branch encloses a shuffle */
@@ -749,6 +821,7 @@ SDFT_B200_PRAGMA_UNROLL(SDFT_B200_EMIT_UNROLL)
     }
   }
   SDFT_B200_STAMP(6);   // warp 0 finished its rows
+  grid_dependency_wait();   // this call completes only after the one before it (see "Between calls")
 }
 #undef stot
 

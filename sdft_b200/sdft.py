@@ -280,5 +280,26 @@ class SDFT:
             raise ValueError("sdft_b200: region of interest outside [0, %d)" % self.size)
         self._rowlen = int(count) if 0 < int(count) < self.size else self.size
 
+    def set_streaming(self, depth):
+        """Streaming mode for endless sequences of short calls on device buffers (the hop loop of
+        test/test.c:69-83): up to `depth` consecutive calls may be in flight at once.  See
+        sdft_b200_set_streaming in include/sdft_b200.h for what the caller promises; depth <= 1 restores plain
+        stream order."""
+        self._lib.sdft_b200_set_streaming(self._h, int(depth))
+        self._check()
+
+    def sdft_hops(self, samples, hop, out):
+        """The reference drivers' hop loop issued from inside the library: `out[h] = sdft(samples[h*hop:(h+1)*hop])`
+        for CUDA tensors `samples` (nhops*hop,) and `out` (nhops, hop, bins)."""
+        assert _is_torch_cuda(samples) and _is_torch_cuda(out) and self.channels == 1
+        assert samples.is_contiguous() and out.is_contiguous() and samples.numel() % hop == 0
+        nhops = samples.numel() // hop
+        assert out.numel() == nhops * hop * self._rowlen
+        self._use_torch_stream(samples)
+        self._f("sdft_hops")(self._h, nhops, int(hop), ctypes.c_void_p(samples.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                             int(hop) * self._rowlen)
+        self._check()
+        return out
+
     def set_chunk(self, chunk):
         self._lib.sdft_b200_set_chunk(self._h, int(chunk))

@@ -191,13 +191,17 @@ def test_randomized_plans_and_call_sequences(SDFT, seed, monkeypatch):
         assert cg == co and np.array_equal(_bits(hg), _bits(ho)) and rel_err(ag, ao) <= TOL[fd]
 
 
-@pytest.mark.parametrize("m,fd", [(16384, "f64"), (10007, "f64"), (10007, "f32"), (8192, "f32")])
+@pytest.mark.parametrize("m,fd", [(16384, "f64"), (10007, "f64"), (10007, "f32"), (8192, "f32"), (65536, "f64"), (65536, "f32")])
 def test_large_and_odd_dft_sizes(SDFT, m, fd):
-    """Big plans (phase table of hundreds of MiB) and an odd prime size (rows not 32-byte aligned: the
-    bin-by-bin store path), over calls that cross the 2m period."""
+    """Big plans and an odd prime size (rows not 32-byte aligned: the bin-by-bin store path), over calls that
+    cross the 2m period.  The reference's plan is O(m) (sdft.h:428-437); ours keeps its phase source O(m) for
+    double (2m roots of unity) and within a fixed budget for float (table stride growing with m)."""
     from oracle import Oracle
     rng = np.random.default_rng(m)
     g = SDFT(m, "blackman", 0.5, td="f32", fd=fd)
+    assert g._lib.sdft_b200_table_bytes(g._h) < 256 << 20
+    if fd == "f64":
+        assert g._lib.sdft_b200_table_bytes(g._h) <= 100 * m          # O(m): 16 B x (m+4 + m + m+4 + 2m)
     o = Oracle("f32", fd, m, "blackman", 0.5)
     for n in (700, 1500, 1):
         x = rng.uniform(-1, 1, n).astype(np.float32)
@@ -210,6 +214,36 @@ def test_large_and_odd_dft_sizes(SDFT, m, fd):
     x3 = rng.uniform(-1, 1, 40).astype(np.float32)
     assert rel_err(g.sdft(x3), o.sdft(x3)) <= TOL[fd]
     assert g.state()[0] == o.state()[0]
+
+
+@pytest.mark.parametrize("budget_mb,m", [(1, 4096), (1, 1000), (2, 10007)])
+def test_float_phase_table_with_a_coarse_stride(SDFT, budget_mb, m, monkeypatch):
+    """The float phase table holds the reference's sequential fiddle recurrence at every `stride`-th cursor
+    and rotates the remainder; a small budget forces strides of 64..1024 on ordinary sizes.  The phase must
+    stay BIT-exact at any cursor and the rows inside the float gate, for calls starting anywhere in the period."""
+    from oracle import Oracle
+    monkeypatch.setenv("SDFT_B200_F0_BUDGET_MB", str(budget_mb))
+    coarse = SDFT(m, "hamming", 0.5, td="f32", fd="f32")
+    monkeypatch.delenv("SDFT_B200_F0_BUDGET_MB")
+    fine = SDFT(m, "hamming", 0.5, td="f32", fd="f32")
+    assert coarse._lib.sdft_b200_table_bytes(coarse._h) < fine._lib.sdft_b200_table_bytes(fine._h)
+    o = Oracle("f32", "f32", m, "hamming", 0.5)
+    rng = np.random.default_rng(seed_of(budget_mb, m))
+    for n in (77, 1500, 2 * m + 333, 1, 900, 31):
+        x = rng.uniform(-1, 1, n).astype(np.float32)
+        want = o.sdft(x)
+        got_c, got_f = coarse.sdft(x), fine.sdft(x)
+        assert rel_err(got_c, want) <= TOL["f32"], (m, n, rel_err(got_c, want))
+        assert rel_err(got_c, got_f) <= 1e-5
+        pc, po = coarse.state()[3], o.state()[3]
+        assert np.array_equal(_bits(pc), _bits(po)), "float modulation phase must be bit-exact at any table stride"
+
+
+def test_oversized_float_plan_is_rejected_with_a_message(SDFT):
+    """A float frequency-domain plan whose phase table cannot fit fails in sdft_alloc with an explanation, not
+    with a cudaMalloc error (the double frequency domain has no such limit)."""
+    with pytest.raises(RuntimeError, match="phase table"):
+        SDFT(1 << 22, "hann", 1, td="f32", fd="f32")
 
 
 def test_reset_and_getters(SDFT):
@@ -464,6 +498,98 @@ def test_fused_roundtrip_batch_and_pieces(SDFT, monkeypatch):
         want = Oracle("f32", "f64", m, "hamming", 0.5).roundtrip(x[c])
         assert np.abs(y[c] - want).max() <= 2e-6
         assert np.abs(y2[c] - want).max() <= 2e-6
+
+
+@pytest.mark.parametrize("fd,depth", [("f64", 4), ("f64", 8), ("f32", 3)])
+def test_streaming_mode_endless_hops(SDFT, fd, depth):
+    """Streaming mode (sdft_b200_set_streaming): 2^20 samples in 256 calls of 4096 on one plan, m = 512 -- the
+    hop loop of test/test.c:69-83 with device buffers (BASELINE config 5's shape), consecutive calls overlapping
+    on the GPU.  The rows must be BIT-identical to the serial mode and inside the gate against the oracle, the
+    state identical at the end."""
+    import torch
+    from oracle import Oracle
+    m, hop, calls = 512, 4096, 256
+    n = hop * calls
+    x = np.random.default_rng(seed_of("stream", fd, depth)).uniform(-1, 1, n).astype(np.float32)
+    xt = torch.from_numpy(x).cuda()
+    cdt = torch.complex128 if fd == "f64" else torch.complex64
+    serial = SDFT(m, "hann", 1, td="f32", fd=fd)
+    want = torch.empty((calls, hop, m), dtype=cdt, device="cuda")
+    for c in range(calls):
+        serial.sdft(xt[c * hop:(c + 1) * hop], out=want[c])
+    torch.cuda.synchronize()
+    flow = SDFT(m, "hann", 1, td="f32", fd=fd)
+    flow.set_streaming(depth)
+    got = torch.zeros((calls, hop, m), dtype=cdt, device="cuda")
+    for c in range(calls):
+        flow.sdft(xt[c * hop:(c + 1) * hop], out=got[c])
+    flow.synchronize()
+    assert torch.equal(torch.view_as_real(got), torch.view_as_real(want))
+    # the same hop loop issued from inside the library
+    hops = SDFT(m, "hann", 1, td="f32", fd=fd)
+    hops.set_streaming(depth)
+    got2 = torch.zeros_like(got)
+    hops.sdft_hops(xt, hop, got2)
+    hops.synchronize()
+    assert torch.equal(torch.view_as_real(got2), torch.view_as_real(want))
+    o = Oracle("f32", fd, m, "hann", 1.0)
+    for c in range(calls):
+        if c in (0, 1, 2, 17, 100, calls - 1):
+            ref = o.sdft(x[c * hop:(c + 1) * hop])
+            assert rel_err(got[c].cpu().numpy(), ref) <= TOL[fd], c
+        else:
+            o.advance(x[c * hop:(c + 1) * hop])
+    for a, b in zip(flow.state(), serial.state()):
+        assert np.array_equal(_bits(np.asarray(a)), _bits(np.asarray(b)))
+    assert rel_err(flow.state()[2], o.state()[2]) <= TOL[fd]
+
+
+@pytest.mark.parametrize("td,fd", [("f32", "f64"), ("f32", "f32"), ("f64", "f64")])
+@pytest.mark.parametrize("window", ["boxcar", "blackman"])
+def test_streaming_mode_mixed_call_sequences(SDFT, td, fd, window):
+    """Streaming with everything the state hand-over has to survive: call sizes below and above the 2m period
+    (short calls roll the history from the previous call's), state-only calls, fused round trips and host-buffer
+    calls (both serial by construction) in between, a reset, a change of depth in mid-stream."""
+    import torch
+    from oracle import Oracle
+    rng = np.random.default_rng(seed_of("mixed", td, fd, window))
+    tdt = torch.float32 if td == "f32" else torch.float64
+    for m in (37, 250, 1024):
+        g = SDFT(m, window, 0.5, td=td, fd=fd)
+        g.set_streaming(5)
+        o = Oracle(td, fd, m, window, 0.5)
+        sizes = [1, 7, 100, 2 * m + 13, 5, 4 * m, 333, 64, 64, 64, 3000, 2, 900]
+        for rnd in range(3):
+            results = []
+            for i, n in enumerate(sizes):
+                x = rng.uniform(-1, 1, n)
+                xt = torch.from_numpy(x).to(tdt).cuda()
+                kind = (i + rnd) % 5
+                if kind == 3:
+                    g.advance(xt)
+                    o.advance(x)
+                elif kind == 4 and i % 2:
+                    y = g.roundtrip(xt)
+                    results.append(("y", y, o.roundtrip(x)))
+                elif kind == 4:
+                    results.append(("rows_host", g.sdft(x), o.sdft(x)))
+                else:
+                    results.append(("rows", g.sdft(xt), o.sdft(x)))
+            g.synchronize()
+            for what, got, ref in results:
+                got = got.cpu().numpy() if hasattr(got, "cpu") else got
+                if what == "y":
+                    assert np.abs(got.astype(np.float64) - ref).max() <= (2e-6 if fd == "f64" else 2e-4) * max(np.abs(ref).max(), 1e-3)
+                else:
+                    assert rel_err(got, ref) <= TOL[fd], (m, rnd, what, rel_err(got, ref))
+            if rnd == 0:
+                g.set_streaming(2)
+            if rnd == 1:
+                g.reset()
+                o.reset()
+        cg, hg, ag, _ = g.state()
+        co, ho, ao, _ = o.state()
+        assert cg == co and np.array_equal(_bits(hg), _bits(ho)) and rel_err(ag, ao) <= TOL[fd]
 
 
 def test_host_tiling_matches_single_pass(SDFT, monkeypatch):
