@@ -491,6 +491,18 @@ def run_b200_arm(args, rank, local_rank, world):
         p._check()
     value = world * args.steps * 4 * n * m / t_analysis
     peak, peak_src = measured_peaks()
+    # ---- roofline denominators of THIS board in THIS run: pure store (the row kernel's own store instruction and
+    # cache policy), pure read (the synthesis kernel's load), copy -- over 16 GiB of the row buffer (>> L2)
+    lib = plans[0]._lib
+    same_run = {}
+    span = min(out.numel() * 16, 16 << 30)
+    for kind, name in ((0, "store"), (1, "read"), (2, "copy")):
+        sus = ctypes.c_double(0.0)
+        best = lib.sdft_b200_measure_hbm(kind, ctypes.c_void_p(out.data_ptr()), span, 6, ctypes.byref(sus))
+        same_run[name] = {"best_GBps": best, "mean_GBps": sus.value}
+    dfma_peak = lib.sdft_b200_measure_dfma(5)
+    launches += 3 * 8 + 7
+    barrier()
     alg_bytes = n * m * 16 + n * 4
     dur = (kms / max(kcount, 1)) * 1e-3
     achieved = alg_bytes / dur / 1e9 if dur > 0 else 0.0
@@ -502,8 +514,18 @@ def run_b200_arm(args, rank, local_rank, world):
             traffic = tj["dram_bytes_per_bin_update"] * n * m
         except Exception:
             traffic = None
+    store_peak = same_run["store"]["best_GBps"] or None
     roofline = {"bound": "hbm", "kernel": "scan_emit_kernel<double> (chunk totals + look-back + row stores, one launch per call)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "static: profiles/emit_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu "
+                                  "--set full capture of this kernel, per bin-update) x this launch's bin-updates",
+                "peak_source": peak_src,
+                "peak_store_same_run": store_peak, "frac_store_peak": (achieved / store_peak) if store_peak else None,
+                "peak_read_same_run": same_run["read"]["best_GBps"], "peak_copy_same_run": same_run["copy"]["best_GBps"],
+                "same_run_peaks": dict(same_run, how="sdft_b200_measure_hbm: pure streaming store (st.global"
+                                       ".L1::no_allocate.L2::evict_first.v4.f64, the row kernel's instruction) / read / copy over "
+                                       "%.0f GiB of device memory, best and mean of 6 launches, CUDA events" % (span / 2 ** 30)),
+                "spec_GBps": 8000.0, "frac_spec": achieved / 8000.0,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dur * 1e3, "launches_timed": kcount,
                 "whole_call_GBps": args.steps * 4 * alg_bytes / t_analysis / 1e9}
 
@@ -522,7 +544,11 @@ def run_b200_arm(args, rank, local_rank, world):
     synth = {"metric": "synthesis_samples_per_s", "value": world * args.steps * n / t_synth, "unit": "samples/s",
              "ms_per_step": t_synth / args.steps * 1e3,
              "roofline": {"bound": "hbm", "achieved": args.steps * alg_bytes / t_synth / 1e9, "peak": peak,
-                          "unit": "GB/s", "frac": args.steps * alg_bytes / t_synth / 1e9 / peak}}
+                          "unit": "GB/s", "frac": args.steps * alg_bytes / t_synth / 1e9 / peak,
+                          "peak_read_same_run": same_run["read"]["best_GBps"],
+                          "frac_read_peak": (args.steps * alg_bytes / t_synth / 1e9 / same_run["read"]["best_GBps"])
+                          if same_run["read"]["best_GBps"] else None,
+                          "spec_GBps": 8000.0, "frac_spec": args.steps * alg_bytes / t_synth / 1e9 / 8000.0}}
     del y
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
@@ -537,6 +563,19 @@ def run_b200_arm(args, rank, local_rank, world):
     n_e = min(args.e2e_n, n)
     xe = torch.from_numpy(x_host[:n_e].copy()).pin_memory()
     oe = torch.empty((n_e, m), dtype=torch.complex128).pin_memory()
+    # the ceiling of this leg on this box: plain pinned device->host copies of the same size, every rank at once
+    src_e = torch.empty((n_e, m), dtype=torch.complex128, device=dev)
+    oe.copy_(src_e, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        oe.copy_(src_e, non_blocking=True)
+    torch.cuda.synchronize()
+    t_pcie = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    pcie_gbps = 3 * n_e * m * 16 / t_pcie / 1e9
+    del src_e
     pe = SDFT(m, "hann", 1, td="f32", fd="f64")
     xep, oep = ctypes.c_void_p(xe.data_ptr()), ctypes.c_void_p(oe.data_ptr())
     for _ in range(max(1, min(args.warmup, 3))):
@@ -551,8 +590,15 @@ def run_b200_arm(args, rank, local_rank, world):
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     barrier()
     pe._check()
+    d2h_gbps = args.steps * n_e * m * 16 / t_e2e / 1e9
     e2e = {"value": world * args.steps * n_e * m / t_e2e, "unit": UNIT, "h2d_bytes_per_step": n_e * 4,
            "d2h_bytes_per_step": n_e * m * 16, "ms_per_step": t_e2e / args.steps * 1e3,
+           "bound": "pcie: the drop-in call delivers 16 B per bin-update to HOST memory; hop_pattern / roundtrip below "
+                    "are what a caller gets who keeps the rows on the device",
+           "d2h_GBps_per_gpu": d2h_gbps, "pcie_ceiling_GBps_per_gpu": pcie_gbps,
+           "pcie_ceiling_GBps_all_gpus": pcie_gbps * world, "frac_of_pcie": d2h_gbps / pcie_gbps,
+           "pcie_ceiling_how": "plain pinned cudaMemcpyAsync device->host of the same %.1f GiB buffer, %d rank(s) "
+                               "concurrently, wall clock, max over ranks" % (n_e * m * 16 / 2 ** 30, world),
            "sample": "sdft_sdft_n(host pinned samples -> host pinned (n, m) rows), n=%d, m=%d, hann; "
                      "PCIe-bound: %.1f GB/s device->host" % (n_e, m, args.steps * n_e * m * 16 / t_e2e / 1e9)}
     launches += pe.launches - e2e_launch0
@@ -595,7 +641,38 @@ def run_b200_arm(args, rank, local_rank, world):
     barrier()
     pr._check()
     launches += pr.launches - rt_launch0
-    e2e["roundtrip"] = {"value": world * args.steps * n_rt * m / t_rt, "unit": UNIT,
+    # the fused kernel alone (device samples in and out): FP64-issue bound; FP64 instructions per bin-update from
+    # the committed ncu capture, the ceiling from a pure DFMA loop timed in this run
+    xd_rt, yd_rt = xr.to(dev), torch.empty(n_rt, dtype=torch.float32, device=dev)
+    fused_launch0 = pr.launches
+    pr._use_torch_stream()
+    for _ in range(2):
+        pr._f("roundtrip_n")(pr._h, n_rt, ctypes.c_void_p(xd_rt.data_ptr()), ctypes.c_void_p(yd_rt.data_ptr()))
+    f0_, f1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0_.record()
+    for _ in range(args.steps):
+        pr._f("roundtrip_n")(pr._h, n_rt, ctypes.c_void_p(xd_rt.data_ptr()), ctypes.c_void_p(yd_rt.data_ptr()))
+    f1_.record()
+    torch.cuda.synchronize()
+    t_fused = f0_.elapsed_time(f1_) * 1e-3 / args.steps
+    pr._check()
+    fused_roofline = None
+    fpath = os.path.join(ROOT, "profiles", "fused_fp64.json")
+    if os.path.exists(fpath) and dfma_peak > 0:
+        try:
+            per = float(json.load(open(fpath))["fp64_thread_instructions_per_bin_update"])
+            ach = per * n_rt * m / t_fused
+            fused_roofline = {"bound": "fp64", "achieved": ach, "peak": dfma_peak, "unit": "FP64 thread-instructions/s",
+                              "frac": ach / dfma_peak, "fp64_instructions_per_bin_update": per,
+                              "device_resident_bin_updates_per_s": n_rt * m / t_fused,
+                              "peak_source": "sdft_b200_measure_dfma: pure DFMA loop on every SM, this run",
+                              "count_source": "static: profiles/fused_fp64.json (smsp__inst_executed_pipe_fp64.sum x 32 / "
+                                              "bin-updates of one ncu capture of the fused kernel)"}
+        except Exception:
+            fused_roofline = None
+    launches += pr.launches - fused_launch0
+    del xd_rt, yd_rt
+    e2e["roundtrip"] = {"roofline": fused_roofline, "value": world * args.steps * n_rt * m / t_rt, "unit": UNIT,
                         "samples_per_s": world * args.steps * n_rt / t_rt,
                         "h2d_bytes_per_step": n_rt * 4, "d2h_bytes_per_step": n_rt * 4,
                         "sample": "sdft_b200_f32f64_roundtrip_n(host samples -> host samples), n=%d, m=%d, hann: "

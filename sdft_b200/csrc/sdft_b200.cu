@@ -159,7 +159,7 @@ extern "C" int sdft_b200_set_streaming(sdft_b200_plan_t* p, unsigned depth)
 {
   if (!p) return SDFT_B200_ERR_ARG;
   if (depth < 1) depth = 1;
-  if (depth > 16) depth = 16;
+  if (depth > 64) depth = 64;
   if (depth == p->stream_depth) return p->status;
   DeviceGuard on_device(p->device);
   if (p->td == kF32 && p->fd == kF32) plan_rings<float, float>(p, depth);

@@ -201,24 +201,17 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
 
   /* Streaming (sdft_b200_set_streaming, depth D > 1): a call that produces rows or only updates the state, reads
    * its samples from device memory and needs little scratch may overlap its predecessors (flow = 1: no wait at
-   * the top of the kernel, hand-over through counters, see sdft_scan.cuh "Between calls").  A serial call waits
-   * for everything before it, so "one serial call, then at most D-1 streaming ones" bounds the calls in flight
-   * to D: the serial call takes scratch slot 0, the streaming ones slots 1 .. D-1, and the state rings have D+1
-   * entries.  Everything else (fused round trips: their finish kernel sits between the scan kernels anyway;
-   * calls with large scratch; the default depth 1) is serial. */
+   * the top of the kernel, hand-over through counters, see sdft_scan.cuh "Between calls").  Call number s takes
+   * scratch slot s % D and first waits until s - D + 1 calls have completed, i.e. until the previous user of its
+   * slot is through: at most D calls are in flight, and the state rings (D + 1 entries, entry s % (D + 1)) never
+   * have a writer and a reader of different calls on one entry.  Everything else (fused round trips: their
+   * finish kernel sits between the scan kernels anyway; calls with large scratch; the default depth 1) is serial:
+   * it waits for all earlier work at the top of the kernel and uses the extra slot D. */
+  const unsigned depth = p->stream_depth;
   const size_t scratch_bytes = 2 * items * wc * sizeof(cx<F>);
-  const bool may_flow = p->stream_depth > 1 && allow_flow && !part && scratch_bytes <= ((size_t)8 << 20);
-  unsigned flow = 0;
-  if (may_flow && p->since_serial + 1 < p->stream_depth)
-  {
-    flow = 1;
-    p->since_serial++;
-  }
-  else
-  {
-    p->since_serial = 0;
-  }
-  const unsigned slot_id = p->since_serial;
+  const unsigned flow = (depth > 1 && allow_flow && !part && scratch_bytes <= ((size_t)8 << 20)) ? 1u : 0u;
+  const unsigned seq = p->calls_issued++;
+  const unsigned slot_id = flow ? seq % depth : depth;
   Plan::Slot& slot = p->slots[slot_id];
   if (!reserve(p, slot.prefix, items * wc * sizeof(cx<F>))) return false;
   if (!reserve(p, slot.chain_totals, items * wc * sizeof(cx<F>))) return false;
@@ -248,9 +241,12 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   a.totals = (cx<F>*)slot.chain_totals.ptr;
   a.flags = (unsigned*)slot.flags.ptr;
   a.error = p->control;
-  a.ticket = p->control + 1 + 3 * slot_id;
-  a.sync = p->control + 2 + 3 * slot_id;
-  a.prev_sync = p->control + 2 + 3 * p->prev_slot;
+  a.completed = p->control + 1;
+  a.completed_target = (seq >= depth) ? seq - depth + 1 : 0;
+  a.ticket = p->control + 2 + 4 * slot_id;
+  a.sync = p->control + 3 + 4 * slot_id;
+  a.finished = p->control + 5 + 4 * slot_id;
+  a.prev_sync = p->control + 3 + 4 * p->prev_slot;
   a.prev_hist_target = p->slots[p->prev_slot].hist_total;
   a.prev_acc_target = p->slots[p->prev_slot].acc_total;
   a.flow = flow;

@@ -53,8 +53,10 @@ namespace sdftb200
  *          previous call has started, compute their deltas and chunk totals while that call is still
  *          streaming rows out, and poll the counters only where the data is needed: the history before the
  *          deltas of the first 2m samples, the accumulators at the head of each chain.  Scratch (ticket,
- *          flags, totals, prefixes) and state buffers rotate through rings sized by the streaming depth, and
- *          every depth-th call is a serial one, which bounds the calls in flight (sdft_launch.hpp).
+ *          flags, totals, prefixes) and state buffers rotate through rings sized by the streaming depth D;
+ *          the plan counts completed calls ([completed], bumped by the last CTA of every call), and a
+ *          streaming call first makes sure that the call D calls back -- the previous user of its slot --
+ *          is among them, which bounds the calls in flight to D (sdft_launch.hpp).
  *      Every thread ends with griddepcontrol.wait: a call completes only after its predecessor has, so work
  *      queued behind the calls in the ordinary way still sees all of them finished.
  * ---------------------------------------------------------------------------------------------- */
@@ -91,6 +93,9 @@ template <typename F> struct ChainArgs
   unsigned prev_hist_target;   // ... and the values they reach once that call has handed over history / accumulators
   unsigned prev_acc_target;
   unsigned flow;           // 1: streaming call, may overlap the previous call (see the header comment); 0: serial
+  unsigned* finished;      // CTAs of this call that are through (this call's slot); the last one rearms it and ...
+  unsigned* completed;     // ... bumps the plan's count of completed calls (calls complete in order)
+  unsigned completed_target;   // streaming: calls that must have completed before this one may touch its slot
   unsigned epoch;
   unsigned total_blocks;   // nblocks * channels * groups
   unsigned nblocks;        // block items per chain: ceil(nchunks / warps per CTA)
@@ -157,6 +162,27 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 __device__ __forceinline__ void grid_dependency_wait()
 {
   asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+/* last instruction of every warp of the scan kernel: keep the order of completion, then count this warp out; the
+ * last warp of the last CTA rearms the slot's counter and bumps the plan's count of completed calls */
+__device__ __forceinline__ void warp_finish(unsigned* s_warps_done, unsigned nwarps, unsigned* finished, unsigned total_blocks,
+                                            unsigned* completed)
+{
+  grid_dependency_wait();
+  __syncwarp();
+  if ((threadIdx.x & 31u) == 0u)
+  {
+    if (atomicAdd(s_warps_done, 1u) == nwarps - 1u)
+    {
+      __threadfence();
+      if (atomicAdd(finished, 1u) == total_blocks - 1u)
+      {
+        *finished = 0;
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(completed), "r"(1u) : "memory");
+      }
+    }
+  }
 }
 __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v)
 {
@@ -429,6 +455,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
    * totals, the carry at the CTA's first chunk */
   extern __shared__ __align__(32) unsigned char smem_raw[];
   __shared__ unsigned s_ticket;
+  __shared__ unsigned s_warps_done;
   const unsigned nwarps = blockDim.x >> 5;
   F* sdelta_all = reinterpret_cast<F*>(smem_raw);
   cx<F>* stot_all = reinterpret_cast<cx<F>*>(smem_raw + (size_t)nwarps * (a.sched.chunk + kDeltaPad) * sizeof(F));
@@ -443,6 +470,8 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   asm volatile("griddepcontrol.launch_dependents;");
   if (threadIdx.x == 0)
   {
+    s_warps_done = 0;
+    if (a.flow) wait_counter(a.completed, a.completed_target, a.error);   // the slot's previous user is through
     const unsigned t = atomicAdd(a.ticket, 1u);
     if (t == a.total_blocks - 1) *a.ticket = 0;   // last ticket of the launch: rearm the slot for its next call
     s_ticket = t;
@@ -707,13 +736,17 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
     }
   }
   SDFT_B200_STAMP(5);   // carries distributed, replay starts
-  if (!valid) { grid_dependency_wait(); return; }
+  if (!valid) { warp_finish(&s_warps_done, nwarps, a.finished, a.total_blocks, a.completed); return; }
 
   /* ---- phase C: replay from the carry and stream the rows out ---- */
   if (EMIT == EMIT_ROWS)
   {
     /* groups without a bin inside the region of interest have done their share (the carries): no rows */
-    if (group * (unsigned)G::SPAN >= roi_end || (group + 1u) * (unsigned)G::SPAN <= roi_first) { grid_dependency_wait(); return; }
+    if (group * (unsigned)G::SPAN >= roi_end || (group + 1u) * (unsigned)G::SPAN <= roi_first)
+    {
+      warp_finish(&s_warps_done, nwarps, a.finished, a.total_blocks, a.completed);
+      return;
+    }
     const size_t row_stride = a.roi_count;
     L.dst = a.out + (size_t)ch * a.out_channel_stride + (size_t)cs.t0 * row_stride + ((long long)e0 - 2 - (long long)roi_first);
     if constexpr (SLIDE)
@@ -821,7 +854,7 @@ SDFT_B200_PRAGMA_UNROLL(SDFT_B200_EMIT_UNROLL)
     }
   }
   SDFT_B200_STAMP(6);   // warp 0 finished its rows
-  grid_dependency_wait();   // this call completes only after the one before it (see "Between calls")
+  warp_finish(&s_warps_done, nwarps, a.finished, a.total_blocks, a.completed);   // completes only after the call before it
 }
 #undef stot
 
