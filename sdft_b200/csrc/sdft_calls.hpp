@@ -269,29 +269,89 @@ bool do_isdft(Plan* p, size_t n, const cx<F>* dfts, T* samples)
   return true;
 }
 
-/* row-pointer variants (sdft.h:622-628, 681-687): rows may be host or device pointers */
+/* ------------------------------------------------------------------------------------------------
+ * row-pointer variants (sdft.h:622-628, 681-687): `n` row pointers, each a host or a device pointer.
+ *
+ * No API call per row.  The pointer list is cut into RUNS of rows that follow one another in memory
+ * (rows[i+1] == rows[i] + bins -- what callers who slice one matrix into rows hand over, e.g. a ring of hop
+ * buffers).  Few long runs: every run is one contiguous call through the same path as sdft_sdft_n /
+ * sdft_isdft_n (straight into device rows, tiled + double-buffered DMA for host rows).  Many short runs
+ * (really scattered rows): the rows are produced in device tiles and moved by ONE scatter/gather kernel per
+ * tile over a device copy of the pointer list (device rows), or by one DMA of the tile to pinned staging and
+ * the library's host copy threads (host rows).
+ * ---------------------------------------------------------------------------------------------- */
+struct RowRun { size_t first, count; };
+
+template <typename P>
+std::vector<RowRun> row_runs(size_t n, P* const* rows, size_t bins)
+{
+  std::vector<RowRun> runs;
+  size_t first = 0;
+  for (size_t i = 1; i <= n; ++i)
+    if (i == n || rows[i] != rows[i - 1] + bins)
+    {
+      runs.push_back({ first, i - first });
+      first = i;
+    }
+  return runs;
+}
+
+bool few_long_runs(size_t nruns, size_t n) { return nruns <= 8 || nruns * 256 <= n; }
+
 template <typename T, typename F>
 bool do_sdft_nd(Plan* p, size_t n, const T* samples, cx<F>** rows_out)
 {
   if (n == 0) return true;
   if (p->channels != 1) { plan_fail(p, SDFT_B200_ERR_ARG, "sdft_nd on a batch plan", __FILE__, __LINE__); return false; }
   DeviceGuard on_device(p->device);
+  const size_t m = row_bins(p), row_bytes = m * sizeof(cx<F>);
+  const std::vector<RowRun> runs = row_runs<cx<F>>(n, rows_out, m);
+  if (few_long_runs(runs.size(), n))
+  {
+    for (const RowRun& r : runs)
+      if (!do_sdft<T, F>(p, r.count, samples + r.first, rows_out[r.first])) return false;
+    return true;
+  }
   bool ok = true;
   const T* x = stage_samples<T>(p, n, samples, &ok);
   if (!ok) return false;
-  const size_t m = row_bins(p), row_bytes = m * sizeof(cx<F>);
   const size_t rows = tile_rows(p, n, row_bytes);
   if (!reserve(p, p->tile[0], rows * row_bytes)) return false;
+  if (!reserve(p, p->row_ptrs, rows * sizeof(void*))) return false;
+  std::vector<CopySeg> segs;
+  std::vector<void*> dev_rows;
   for (size_t t0 = 0; t0 < n; t0 += rows)
   {
     const size_t len = (t0 + rows <= n) ? rows : n - t0;
     if (!analysis_device<T, F>(p, len, x + t0, n, (cx<F>*)p->tile[0].ptr, len * m)) return false;
+    /* rows of this tile by memory kind (one query per run start would do; scattered rows are their own runs) */
+    dev_rows.assign(len, nullptr);
+    size_t ndev = 0;
     for (size_t i = 0; i < len; ++i)
+      if (classify(rows_out[t0 + i]) == kDevice) { dev_rows[i] = rows_out[t0 + i]; ++ndev; }
+    if (ndev)
     {
-      CU_TRY(p, cudaMemcpyAsync(rows_out[t0 + i], (cx<F>*)p->tile[0].ptr + i * m, row_bytes, cudaMemcpyDefault, p->stream));
+      CU_TRY(p, cudaMemcpyAsync(p->row_ptrs.ptr, dev_rows.data(), len * sizeof(void*), cudaMemcpyHostToDevice, p->stream));
+      size_t blocks = (len * m + 255) / 256;
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      scatter_rows_kernel<F><<<(unsigned)blocks, 256, 0, p->stream>>>((const cx<F>*)p->tile[0].ptr, (cx<F>* const*)p->row_ptrs.ptr,
+                                                                       len, (unsigned)m);
+      p->launches++;
+      CU_TRY(p, cudaGetLastError());
     }
-    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    if (ndev < len)
+    {
+      if (!reserve_stage(p, 0, rows * row_bytes)) return false;
+      CU_TRY(p, cudaMemcpyAsync(p->stage[0], p->tile[0].ptr, len * row_bytes, cudaMemcpyDeviceToHost, p->stream));
+      CU_TRY(p, cudaStreamSynchronize(p->stream));
+      segs.clear();
+      for (size_t i = 0; i < len; ++i)
+        if (!dev_rows[i]) segs.push_back({ rows_out[t0 + i], (const char*)p->stage[0] + i * row_bytes, row_bytes });
+      HostCopier::get().run(segs);
+    }
+    CU_TRY(p, cudaStreamSynchronize(p->stream));      // dev_rows / the tile are reused by the next tile
   }
+  p->samples_in_flight = false;
   return true;
 }
 
@@ -302,8 +362,16 @@ bool do_isdft_nd(Plan* p, size_t n, const cx<F>** rows_in, T* samples)
   if (p->channels != 1) { plan_fail(p, SDFT_B200_ERR_ARG, "isdft_nd on a batch plan", __FILE__, __LINE__); return false; }
   DeviceGuard on_device(p->device);
   const size_t m = row_bins(p), row_bytes = m * sizeof(cx<F>);
+  const std::vector<RowRun> runs = row_runs<const cx<F>>(n, rows_in, m);
+  if (few_long_runs(runs.size(), n))
+  {
+    for (const RowRun& r : runs)
+      if (!do_isdft<T, F>(p, r.count, rows_in[r.first], samples + r.first)) return false;
+    return true;
+  }
   const size_t rows = tile_rows(p, n, row_bytes);
   if (!reserve(p, p->tile[0], rows * row_bytes)) return false;
+  if (!reserve(p, p->row_ptrs, rows * sizeof(void*))) return false;
   const bool out_dev = classify(samples) == kDevice;
   T* y = samples;
   if (!out_dev)
@@ -311,12 +379,43 @@ bool do_isdft_nd(Plan* p, size_t n, const cx<F>** rows_in, T* samples)
     if (!reserve(p, p->synth_out, n * sizeof(T))) return false;
     y = (T*)p->synth_out.ptr;
   }
+  std::vector<CopySeg> segs;
+  std::vector<const void*> dev_rows;
   for (size_t t0 = 0; t0 < n; t0 += rows)
   {
     const size_t len = (t0 + rows <= n) ? rows : n - t0;
+    dev_rows.assign(len, nullptr);
+    size_t ndev = 0;
     for (size_t i = 0; i < len; ++i)
+      if (classify(rows_in[t0 + i]) == kDevice) { dev_rows[i] = rows_in[t0 + i]; ++ndev; }
+    if (ndev < len)
     {
-      CU_TRY(p, cudaMemcpyAsync((cx<F>*)p->tile[0].ptr + i * m, rows_in[t0 + i], row_bytes, cudaMemcpyDefault, p->stream));
+      /* host rows: gathered into pinned staging by the copy threads, one DMA into the tile */
+      if (!reserve_stage(p, 0, rows * row_bytes)) return false;
+      segs.clear();
+      for (size_t i = 0; i < len; ++i)
+        if (!dev_rows[i]) segs.push_back({ (char*)p->stage[0] + i * row_bytes, rows_in[t0 + i], row_bytes });
+      HostCopier::get().run(segs);
+      if (ndev == 0)
+      {
+        CU_TRY(p, cudaMemcpyAsync(p->tile[0].ptr, p->stage[0], len * row_bytes, cudaMemcpyHostToDevice, p->stream));
+      }
+      else
+      {
+        for (const CopySeg& sgm : segs)     // mixed tile: only the host rows' slots are uploaded
+          CU_TRY(p, cudaMemcpyAsync((char*)p->tile[0].ptr + ((char*)sgm.dst - (char*)p->stage[0]), sgm.dst, row_bytes,
+                                    cudaMemcpyHostToDevice, p->stream));
+      }
+    }
+    if (ndev)
+    {
+      CU_TRY(p, cudaMemcpyAsync(p->row_ptrs.ptr, dev_rows.data(), len * sizeof(void*), cudaMemcpyHostToDevice, p->stream));
+      size_t blocks = (len * m + 255) / 256;
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      gather_rows_kernel<F><<<(unsigned)blocks, 256, 0, p->stream>>>((cx<F>*)p->tile[0].ptr, (const cx<F>* const*)p->row_ptrs.ptr,
+                                                                      len, (unsigned)m);
+      p->launches++;
+      CU_TRY(p, cudaGetLastError());
     }
     if (!synthesis_device<T, F>(p, len, (const cx<F>*)p->tile[0].ptr, len * m, y + t0, n)) return false;
     CU_TRY(p, cudaStreamSynchronize(p->stream));

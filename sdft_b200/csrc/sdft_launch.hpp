@@ -93,8 +93,11 @@ unsigned choose_chunk_free(const Plan* p, size_t n, int geo)
   if (geo == GEO_NARROW)
   {
     /* profiles/r01_geo_sweep.md: narrow warps like longer chunks earlier, but never so long that a chain
-     * has fewer than 16 chunks */
+     * has fewer than 16 chunks.  Streaming calls overlap their neighbours, so the latency of a chunk's serial
+     * steps hides behind other calls' work and the per-chunk overheads decide: 128 from the start
+     * (profiles/r02_stream_sweep.md: 6.7 us instead of 7.3-7.8 per 4096-sample call at m = 512) */
     unsigned c = (u < 16384.0) ? 32u : ((u < 30.0e3) ? 64u : 128u);
+    if (p->stream_depth > 1 && c < 128u) c = 128u;
     while (c > 32u && (size_t)c * 16 > n) c >>= 1;
     return c;
   }
@@ -241,7 +244,8 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   a.totals = (cx<F>*)slot.chain_totals.ptr;
   a.flags = (unsigned*)slot.flags.ptr;
   a.error = p->control;
-  a.completed = p->control + 1;
+  a.handover = depth > 1 ? 1u : 0u;
+  a.completed = depth > 1 ? p->control + 1 : nullptr;
   a.completed_target = (seq >= depth) ? seq - depth + 1 : 0;
   a.ticket = p->control + 2 + 4 * slot_id;
   a.sync = p->control + 3 + 4 * slot_id;

@@ -65,6 +65,7 @@ struct sdft_b200_plan
   void* phase_scratch = nullptr;   // cells complex values, introspection only
 
   Buffer samples, synth_out, tile[2], part, weights;
+  Buffer row_ptrs;               // device copy of one tile's row pointers (sdft_sdft_nd / sdft_isdft_nd, scattered rows)
   Buffer syn_ab;                 // fused synthesis: per-bin (A, B) weights with the window folded in (make_synth_weights)
   bool syn_ab_ready = false, syn_ab_unit = false;
   Buffer trace;                  // -DSDFT_B200_TRACE builds: per-CTA phase stamps of the last scan launch
@@ -249,6 +250,7 @@ template <typename F> PhaseSource<F> phase_source(const sdft_b200_plan* p)
   s.cells = (unsigned)p->cells;
   s.m = (unsigned)p->m;
   s.period = (unsigned)(2 * p->m);
+  s.inv_period = ~0ull / (unsigned long long)(2 * p->m);
   s.stride = p->f0_stride;
   for (int q = 0; q < 4; ++q)
   {
@@ -414,7 +416,7 @@ void plan_destroy(Plan* p)
     for (Buffer* b : { &s.prefix, &s.chain_totals, &s.flags })
       if (b->ptr) cudaFree(b->ptr);
   void* ptrs[] = { p->tw_ext, p->tws, p->f0, p->roots, p->phase_scratch, p->control,
-                   p->samples.ptr, p->synth_out.ptr, p->part.ptr, p->weights.ptr, p->syn_ab.ptr, p->trace.ptr, p->tile[0].ptr, p->tile[1].ptr };
+                   p->samples.ptr, p->synth_out.ptr, p->row_ptrs.ptr, p->part.ptr, p->weights.ptr, p->syn_ab.ptr, p->trace.ptr, p->tile[0].ptr, p->tile[1].ptr };
   for (void* q : ptrs)
     if (q) cudaFree(q);
   for (int w = 0; w < 2; ++w)

@@ -93,6 +93,8 @@ template <typename F> struct ChainArgs
   unsigned prev_hist_target;   // ... and the values they reach once that call has handed over history / accumulators
   unsigned prev_acc_target;
   unsigned flow;           // 1: streaming call, may overlap the previous call (see the header comment); 0: serial
+  unsigned handover;       // 1: plan in streaming mode -- keep the hand-over and completion counters (a later call may
+                           // poll them); 0: every call on the plan is serial, nobody ever looks
   unsigned* finished;      // CTAs of this call that are through (this call's slot); the last one rearms it and ...
   unsigned* completed;     // ... bumps the plan's count of completed calls (calls complete in order)
   unsigned completed_target;   // streaming: calls that must have completed before this one may touch its slot
@@ -169,6 +171,7 @@ __device__ __forceinline__ void warp_finish(unsigned* s_warps_done, unsigned nwa
                                             unsigned* completed)
 {
   grid_dependency_wait();
+  if (!completed) return;       // plan not in streaming mode: nobody counts calls
   __syncwarp();
   if ((threadIdx.x & 31u) == 0u)
   {
@@ -517,9 +520,12 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   {
     if (a.td_double) roll_history<double, F>(a, ch, jb);
     else roll_history<float, F>(a, ch, jb);
-    /* hand-over: this CTA's piece of the next call's history is written */
-    __syncthreads();
-    if (threadIdx.x == 0) red_release_add_u32(a.sync, 1u);
+    if (a.handover)
+    {
+      /* hand-over: this CTA's piece of the next call's history is written */
+      __syncthreads();
+      if (threadIdx.x == 0) red_release_add_u32(a.sync, 1u);
+    }
   }
   __syncwarp();
   SDFT_B200_STAMP(1);   // deltas in shared memory
@@ -711,9 +717,12 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
         for (int b = 0; b < G::CPL; ++b)
           if (live[b]) ao[e0 + b] = agg[b];
       }
-      /* hand-over: this chain's accumulators are in place for the next call */
-      __syncwarp();
-      if (lane == 0) red_release_add_u32(a.sync + 1, 1u);
+      if (a.handover)
+      {
+        /* hand-over: this chain's accumulators are in place for the next call */
+        __syncwarp();
+        if (lane == 0) red_release_add_u32(a.sync + 1, 1u);
+      }
     }
 #pragma unroll
     for (int b = 0; b < G::CPL; ++b) L.acc[b] = carry[b];

@@ -32,6 +32,7 @@ template <typename F> struct PhaseSource
   unsigned cells;
   unsigned m;
   unsigned period;        // 2m
+  unsigned long long inv_period;   // floor((2^64 - 1) / 2m): (c k) mod 2m by one multiply-high instead of a 64-bit division
   unsigned stride;        // cursors per table row (float)
   int mir_cell[4];        // mirror cells (sdft.h:589-595): cell index, source CELL (-1: always zero), conjugated?
   int mir_src[4];
@@ -75,7 +76,10 @@ __device__ __forceinline__ cx<F> phase_at(const PhaseSource<F>& s, int e, unsign
         return z;
       }
     }
-    const unsigned long long j = ((unsigned long long)cursor * (unsigned long long)(cell - 2)) % s.period;
+    const unsigned long long x = (unsigned long long)cursor * (unsigned long long)(cell - 2);    // < 2^61
+    unsigned long long j = x - __umul64hi(x, s.inv_period) * s.period;                            // x mod 2m, up to + 2m
+    if (j >= s.period) j -= s.period;
+    if (j >= s.period) j -= s.period;
     cx<F> p = s.roots[j];
     if (conj) p.i = -p.i;
     return p;

@@ -195,4 +195,29 @@ __global__ void convolve_kernel(const cx<F>* __restrict__ in, cx<F>* __restrict_
   }
 }
 
+/* scattered row pointers (sdft_sdft_nd / sdft_isdft_nd, sdft.h:622-628, :681-687): tile (rows, m) <-> rows[r][0..m),
+ * rows with a null pointer are skipped (they live in host memory and take the staging path) */
+template <typename F>
+__global__ void scatter_rows_kernel(const cx<F>* __restrict__ tile, cx<F>* const* __restrict__ rows, unsigned long long nrows, unsigned m)
+{
+  const unsigned long long total = nrows * m, stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride)
+  {
+    const unsigned long long r = idx / m;
+    cx<F>* dst = rows[r];
+    if (dst) dst[idx - r * m] = tile[idx];
+  }
+}
+template <typename F>
+__global__ void gather_rows_kernel(cx<F>* __restrict__ tile, const cx<F>* const* __restrict__ rows, unsigned long long nrows, unsigned m)
+{
+  const unsigned long long total = nrows * m, stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride)
+  {
+    const unsigned long long r = idx / m;
+    const cx<F>* src = rows[r];
+    if (src) tile[idx] = src[idx - r * m];
+  }
+}
+
 }  // namespace sdftb200

@@ -210,6 +210,7 @@ def test_large_and_odd_dft_sizes(SDFT, m, fd):
         # chunk per call with the float recurrence in the totals too (the literal mode) must be BIT-exact, which
         # pins the strided phase table; the tolerance comparison follows once the window has filled.
         import os
+        import torch
         os.environ["SDFT_B200_F32"] = "strict"
         try:
             lit = SDFT(m, "blackman", 0.5, td="f32", fd=fd)
@@ -217,10 +218,18 @@ def test_large_and_odd_dft_sizes(SDFT, m, fd):
             del os.environ["SDFT_B200_F32"]
         lit.set_chunk(1024)
         o2 = Oracle("f32", fd, m, "blackman", 0.5)
+        # device rows: one launch, one chunk (host rows would be produced in 128 MiB tiles = several calls)
         x0 = rng.uniform(-1, 1, 700).astype(np.float32)
-        assert np.array_equal(_bits(lit.sdft(x0)), _bits(o2.sdft(x0)))
-        x1 = rng.uniform(-1, 1, 300).astype(np.float32)          # starts at cursor 700: off the table grid
-        assert np.array_equal(_bits(lit.sdft(x1)), _bits(o2.sdft(x1)))
+        assert np.array_equal(_bits(lit.sdft(torch.from_numpy(x0).cuda()).cpu().numpy()), _bits(o2.sdft(x0)))
+        lit.reset()
+        o2.reset()
+        x1 = rng.uniform(-1, 1, 1000).astype(np.float32)
+        lit.advance(x1[:700])                                    # the next call starts at cursor 700: off the table grid
+        o2.advance(x1[:700])
+        got1 = lit.sdft(torch.from_numpy(x1[700:]).cuda()).cpu().numpy()
+        want1 = o2.sdft(x1[700:])
+        assert rel_err(got1, want1) <= 1e-6                      # the carry of the state-only call is summed in its own order
+        assert np.array_equal(_bits(lit.state()[3]), _bits(o2.state()[3])), "phase after 1000 samples, table stride 512"
         del lit, o2
     else:
         for n in (700, 1500, 1):
@@ -313,6 +322,54 @@ def test_single_sample_and_row_pointer_variants(SDFT):
     y = np.empty(len(rows), np.float32)
     lib.sdft_b200_f32f64_isdft_nd(g._h, len(rows), ptrs, y.ctypes.data_as(ctypes.c_void_p))
     assert np.abs(y - o.isdft(want[10:])).max() <= 2e-6
+
+
+@pytest.mark.parametrize("layout", ["contiguous", "runs", "scattered_host", "scattered_device", "mixed"])
+def test_row_pointer_variants_at_size(SDFT, layout):
+    """sdft_sdft_nd / sdft_isdft_nd (sdft.h:622-628, :681-687) at n = 2^16, m = 1024 for every way a caller can
+    lay its rows out: slices of one matrix (one run), a ring of hop buffers (a few long runs), rows scattered
+    through host memory, through device memory, and both kinds in one call.  Against sdft_sdft_n / sdft_isdft_n
+    of a twin plan (bit-identical: same kernels, only the destination differs) and the oracle on a sample."""
+    import torch
+    from oracle import Oracle
+    m, n = 1024, 1 << 16
+    x = np.random.default_rng(seed_of("nd", layout)).uniform(-1, 1, n).astype(np.float32)
+    twin = SDFT(m, "hann", 0.5, td="f32", fd="f64")
+    want = twin.sdft(x)
+    want_y = twin.isdft(want)
+    g = SDFT(m, "hann", 0.5, td="f32", fd="f64")
+    lib = g._lib
+    perm = np.random.default_rng(5).permutation(n)
+    host = np.zeros((n, m), np.complex128)
+    dev = torch.zeros((n, m), dtype=torch.complex128, device="cuda")
+    if layout == "contiguous":
+        addr = [host.ctypes.data + i * m * 16 for i in range(n)]
+    elif layout == "runs":                       # 16 hop buffers of 4096 rows, in shuffled order
+        order = np.random.default_rng(6).permutation(16)
+        addr = [host.ctypes.data + (int(order[i // 4096]) * 4096 + i % 4096) * m * 16 for i in range(n)]
+    elif layout == "scattered_host":
+        addr = [host.ctypes.data + int(perm[i]) * m * 16 for i in range(n)]
+    elif layout == "scattered_device":
+        addr = [dev.data_ptr() + int(perm[i]) * m * 16 for i in range(n)]
+    else:
+        addr = [(dev.data_ptr() if perm[i] % 2 else host.ctypes.data) + int(perm[i]) * m * 16 for i in range(n)]
+    ptrs = (ctypes.c_void_p * n)(*addr)
+    lib.sdft_b200_f32f64_sdft_nd(g._h, n, x.ctypes.data_as(ctypes.c_void_p), ptrs)
+    g.synchronize()
+    dev_h = dev.cpu().numpy()
+    base_h, base_d = host.ctypes.data, dev.data_ptr()
+    idx = np.array([((a - base_d) if (layout in ("scattered_device", "mixed") and base_d <= a < base_d + n * m * 16) else (a - base_h)) // (m * 16)
+                    for a in addr])
+    on_dev = np.array([layout in ("scattered_device", "mixed") and base_d <= a < base_d + n * m * 16 for a in addr])
+    got = np.where(on_dev[:, None], dev_h[idx], host[idx])
+    assert np.array_equal(_bits(got), _bits(want))
+    y = np.zeros(n, np.float32)
+    lib.sdft_b200_f32f64_isdft_nd(g._h, n, ptrs, y.ctypes.data_as(ctypes.c_void_p))
+    g._check()
+    assert np.array_equal(_bits(y), _bits(want_y))
+    o = Oracle("f32", "f64", m, "hann", 0.5)
+    ref = o.sdft(x[:3000])
+    assert rel_err(got[:3000], ref) <= 1e-9
 
 
 def test_device_pointers_and_batch(SDFT):
