@@ -212,7 +212,7 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
    * it waits for all earlier work at the top of the kernel and uses the extra slot D. */
   const unsigned depth = p->stream_depth;
   const size_t scratch_bytes = 2 * items * wc * sizeof(cx<F>);
-  const unsigned flow = (depth > 1 && allow_flow && !part && scratch_bytes <= ((size_t)8 << 20)) ? 1u : 0u;
+  const unsigned flow = (depth > 1 && allow_flow && !part && scratch_bytes <= ((size_t)32 << 20)) ? 1u : 0u;
   const unsigned seq = p->calls_issued++;
   const unsigned slot_id = flow ? seq % depth : depth;
   Plan::Slot& slot = p->slots[slot_id];

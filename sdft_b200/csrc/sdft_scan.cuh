@@ -307,9 +307,9 @@ __device__ __forceinline__ void cp_async_wait_all()
 /* the plan's accumulators at the start of this call (one warp, this lane's cells e0 .. e0+CPL-1).  A streaming
  * call may get here while the previous call is still adding up: wait for its accumulator rows first. */
 template <typename F, int CPL>
-__device__ __forceinline__ void load_plan_acc(const ChainArgs<F>& a, unsigned ch, int e0, unsigned lane, cx<F>* acc)
+__device__ __forceinline__ void load_plan_acc(const ChainArgs<F>& a, unsigned ch, int e0, unsigned lane, cx<F>* acc, bool wait)
 {
-  if (a.flow)
+  if (wait)
   {
     if (lane == 0) wait_counter(a.prev_sync + 1, a.prev_acc_target, a.error);
     __syncwarp();
@@ -335,6 +335,8 @@ template <typename F, int GEO>
 __device__ __forceinline__ void look_back(const ChainArgs<F>& a, size_t item, size_t item_stride, unsigned jb, unsigned lane,
                                           unsigned ch, int e0, cx<F>* stage, unsigned stage_rows, cx<F>* acc, unsigned trace_slot)
 {
+  /* `acc` arrives holding the plan's accumulators when the call is serial (loaded before the walk so that the
+   * latency hides behind it); a streaming call fetches them only if the walk ends at the chain's start */
   typedef Geo<F, GEO> G;
   typedef Arith<F> A;
   const unsigned code_total = a.epoch * 2u, code_prefix = a.epoch * 2u + 1u;
@@ -396,7 +398,7 @@ __device__ __forceinline__ void look_back(const ChainArgs<F>& a, size_t item, si
   const size_t rstride = item_stride * G::WC;
   if (from_start)
   {
-    load_plan_acc<F, G::CPL>(a, ch, e0, lane, acc);
+    if (a.flow) load_plan_acc<F, G::CPL>(a, ch, e0, lane, acc, true);
   }
   else
   {
@@ -672,8 +674,8 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
     }
     SDFT_B200_STAMP(3);   // aggregate published
     cx<F> carry[G::CPL];
+    if (!a.flow || jb == 0) load_plan_acc<F, G::CPL>(a, ch, e0, lane, carry, a.flow != 0);
     if (jb > 0) look_back<F, GEO>(a, item, item_stride, jb, lane, ch, e0, sstage, a.stage_rows, carry, ticket);
-    else load_plan_acc<F, G::CPL>(a, ch, e0, lane, carry);
     SDFT_B200_STAMP(4);   // carry known
 #pragma unroll
     for (int b = 0; b < G::CPL; ++b) agg[b] = A::cadd(carry[b], agg[b]);

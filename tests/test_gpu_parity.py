@@ -245,7 +245,7 @@ def test_large_and_odd_dft_sizes(SDFT, m, fd):
     assert g.state()[0] == o.state()[0]
 
 
-@pytest.mark.parametrize("budget_mb,m", [(1, 4096), (1, 1000), (2, 10007)])
+@pytest.mark.parametrize("budget_mb,m", [(1, 4096), (0, 1000), (2, 10007)])
 def test_float_phase_table_with_a_coarse_stride(SDFT, budget_mb, m, monkeypatch):
     """The float phase table holds the reference's sequential fiddle recurrence at every `stride`-th cursor
     and rotates the remainder; a small budget forces strides of 64..1024 on ordinary sizes.  The phase must
