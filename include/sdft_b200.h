@@ -147,7 +147,9 @@ SDFT_B200_API int sdft_b200_set_stream(sdft_b200_plan_t* plan, void* cuda_stream
  * DEVICE rows may be in flight at once: a call starts computing while its predecessors still stream their rows
  * out, and takes the history and the accumulators over through device-side counters instead of a kernel
  * boundary (a 4096-sample call at dftsize 512 otherwise spends most of its time on start-up and drain
- * latencies).  Results are bit-identical to the serial mode.  What the caller promises while depth > 1:
+ * latencies).  Results do not depend on timing; with the same chunk length they are bit-identical to the serial
+ * mode (a streaming plan picks longer chunks by default, which changes the order in which carries are added:
+ * ~1e-13 for double, ~1e-6 for float data).  What the caller promises while depth > 1:
  *   - the samples of a call are complete in device memory when the call is ISSUED (written by work that was
  *     synchronised with the host or finished before the previous library call was issued), not merely ordered
  *     before it on the stream;

@@ -168,8 +168,45 @@ def testwav_cases():
     print("testwav.npz: n =", n, "snr =", float(out["c1_snr_db"]), "dB")
 
 
+def chirp_late_rows():
+    """BASELINE config 3 at FULL length: the 2^26-sample chirp, m = 2048, float FD, hann, latency 0.5, run
+    continuously through the compiled reference (the parity build, ~15 CPU-minutes on one core; rows are produced
+    in 4096-sample tiles and dropped).  Kept: 4 rows right after the 8-way time-shard boundaries 2, 4, 6 and 7
+    and the last 4 rows of the signal -- where the float accumulators have walked longest -- plus the samples
+    the reference synthesizes from them.  Pins the long-run float path: tests/test_gpu_configs.py compares the
+    continuous GPU run and the halo-primed shards with these rows at 1e-4."""
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from sdft_b200 import workloads
+    n, m, tile, keep = 1 << 26, 2048, 4096, 4
+    probes = [k * (n // 8) for k in (2, 4, 6, 7)] + [n - keep]
+    r = Ref("f32", "f32", m, 1, 0.5)
+    rows, ys = {}, {}
+    pos = 0
+    import time
+    t0 = time.time()
+    while pos < n:
+        x = workloads.chirp(n, pos, tile)
+        d = r.sdft(x)
+        for p in probes:
+            if pos <= p < pos + tile:
+                assert p + keep <= pos + tile
+                rows[p] = d[p - pos:p - pos + keep].copy()
+                ys[p] = r.isdft(rows[p])
+        pos += tile
+        if (pos // tile) % 1024 == 0:
+            print("chirp: %d / %d samples, %.0f s" % (pos, n, time.time() - t0), flush=True)
+    out = {"n": np.array(n), "m": np.array(m), "probes": np.array(probes, np.int64),
+           "rows": np.stack([rows[p] for p in probes]), "y": np.stack([ys[p] for p in probes]),
+           "final_cursor": np.array(r.state()[0])}
+    np.savez_compressed(os.path.join(HERE, "c3_chirp_late.npz"), **out)
+    print("c3_chirp_late.npz written in %.0f s" % (time.time() - t0))
+
+
 if __name__ == "__main__":
     build(want_ref=True)
+    if "--chirp" in sys.argv:          # the long one, on request only
+        chirp_late_rows()
+        sys.exit(0)
     small_cases()
     table_cases()
     python_cases()
