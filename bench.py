@@ -208,6 +208,13 @@ def cpu_reference_run(samples_per_window, threads, steps, warmup):
     return agg, per_step, kind, single
 
 
+def cpu_build(kind):
+    import oracle
+    if kind == "reference":
+        return "unmodified c/src/sdft/sdft.h, gcc -std=gnu99 -DSDFT_NO_COMPLEX_H %s (oracle/Makefile)" % oracle.fast_flags()
+    return "oracle port, gcc -O2 -ffp-contract=off"
+
+
 def cpu_hop_pattern(samples, threads):
     """The reference's own usage pattern (test/test.c:79-80): sdft_sdft_n followed by sdft_isdft_n on the
     same hop buffer, one channel per host thread, hann.  Returns analysis bin-updates/s (synthesis time included)."""
@@ -255,7 +262,7 @@ def run_reference_arm(args, rank, world):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "configs[1]: white noise, m=4096, f32 TD / f64 FD, four windows; reference C "
                                "sdft_sdft_n on host cores, bounded sample", "m": M, "sample": sample},
-        "cpu_baseline": {"value": agg, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+        "cpu_baseline": {"value": agg, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample, "build": cpu_build(kind),
                          "single_thread": single, "synthesis_samples_per_s": SYNTH.get("all"),
                          "synthesis_single_thread_samples_per_s": SYNTH.get("single")},
         "e2e": {"value": agg, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
@@ -743,7 +750,7 @@ def run_b200_arm(args, rank, local_rank, world):
         threads = os.cpu_count() or 1
         spw = 4096
         agg, per_step, kind, single = cpu_reference_run(spw, threads, 2, 1)
-        cpu = {"value": agg, "unit": UNIT, "cores": threads, "kind": kind, "single_thread": single,
+        cpu = {"value": agg, "unit": UNIT, "cores": threads, "kind": kind, "single_thread": single, "build": cpu_build(kind),
                "synthesis_samples_per_s": SYNTH.get("all"), "synthesis_single_thread_samples_per_s": SYNTH.get("single"),
                "sample": "%d host threads x 4 windows x %d samples, one channel per thread, m=%d" % (threads, spw, m)}
 

@@ -39,6 +39,27 @@ def build(want_ref=True):
     subprocess.run(["make", "-s", "-C", HERE] + targets, check=True)
 
 
+def _cpu_has_avx512():
+    """x86-64-v4: what the _fast512 timing build of the reference needs"""
+    try:
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags")).split()
+    except (OSError, StopIteration):
+        return False
+    return all(f in flags for f in ("avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"))
+
+
+def fast_suffix():
+    """Timing build of the reference for THIS host: x86-64-v4 when the CPU has AVX-512 and the library was built,
+    else x86-64-v3 (what -O3 -march=native, BASELINE.md, comes to on the two kinds of host this runs on)."""
+    if _cpu_has_avx512() and os.path.exists(os.path.join(REF_DIR, "libsdft_ref_f32f64_fast512.so")):
+        return "_fast512"
+    return "_fast"
+
+
+def fast_flags():
+    return "-O3 -march=x86-64-v4" if fast_suffix() == "_fast512" else "-O3 -march=x86-64-v3"
+
+
 def have_ref(fast=False):
     name = "libsdft_ref_f32f64%s.so" % ("_fast" if fast else "")
     return os.path.exists(os.path.join(REF_DIR, name))
@@ -160,7 +181,7 @@ class Ref(_Base):
     """The reference's own C implementation (c/src/sdft/sdft.h via oracle/ref_shim.c)."""
 
     def __init__(self, td, fd, m, window="hann", latency=1.0, fast=False):
-        path = os.path.join(REF_DIR, "libsdft_ref_%s%s%s.so" % (td, fd, "_fast" if fast else ""))
+        path = os.path.join(REF_DIR, "libsdft_ref_%s%s%s.so" % (td, fd, fast_suffix() if fast else ""))
         if not os.path.exists(path):
             build(want_ref=True)
         if not os.path.exists(path):

@@ -212,7 +212,11 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
    * it waits for all earlier work at the top of the kernel and uses the extra slot D. */
   const unsigned depth = p->stream_depth;
   const size_t scratch_bytes = 2 * items * wc * sizeof(cx<F>);
-  const unsigned flow = (depth > 1 && allow_flow && !part && scratch_bytes <= ((size_t)32 << 20)) ? 1u : 0u;
+  /* overlap pays where a call's fixed latencies (ticket, first look-back, drain: ~10 us) are a visible share of
+   * it: up to ~2^28 bin-updates (0.7 ms).  Longer calls gain nothing and one shape was measured slower
+   * (profiles/r02_v1_mid_sweep.md: m = 4096 float, 2^18 samples per call), so they stay serial. */
+  const bool short_call = (double)n * (double)m * (double)ch <= 268435456.0;
+  const unsigned flow = (depth > 1 && allow_flow && !part && short_call && scratch_bytes <= ((size_t)32 << 20)) ? 1u : 0u;
   const unsigned seq = p->calls_issued++;
   const unsigned slot_id = flow ? seq % depth : depth;
   Plan::Slot& slot = p->slots[slot_id];

@@ -172,6 +172,47 @@ def test_config3_full_size_shard_independence(torch_cuda):
     print("config 3: SNR %.2f dB (1 shard) / %.2f dB (8 shards)" % (s1, s8))
 
 
+def test_config3_full_size_against_reference_rows(torch_cuda, golden_dir):
+    """The long-run float path pinned to the REFERENCE: tests/golden/c3_chirp_late.npz holds rows the compiled
+    reference produced after running continuously through the 2^26-sample chirp (m = 2048, float FD, hann,
+    latency 0.5; tests/golden/make_golden.py --chirp) -- right after the 8-way shard boundaries 2, 4, 6, 7 and
+    at the very end, where its float accumulators have walked longest (growth ~ sqrt(t)).  Compared at the float
+    gate with (a) ONE continuous GPU run and (b) the halo-primed plan of each time shard; the samples
+    synthesized from those rows as well."""
+    import os
+    torch = torch_cuda
+    from sdft_b200 import SDFT
+    path = os.path.join(golden_dir, "c3_chirp_late.npz")
+    if not os.path.exists(path):
+        pytest.skip("c3_chirp_late.npz not generated")
+    g = np.load(path)
+    n, m = int(g["n"]), int(g["m"])
+    probes, keep = [int(p) for p in g["probes"]], g["rows"].shape[1]
+    assert (n, m) == (1 << 26, 2048)
+    x = torch.from_numpy(workloads.chirp(n)).cuda()
+    scale = float(np.abs(g["rows"]).max())
+    cont = SDFT(m, "hann", 0.5, td="f32", fd="f32")
+    pos, worst_c, worst_s = 0, 0.0, 0.0
+    for i, p in enumerate(probes):
+        cont.advance(x[pos:p])
+        rows = cont.sdft(x[p:p + keep])
+        pos = p + keep
+        got = rows.cpu().numpy()
+        worst_c = max(worst_c, np.abs(got - g["rows"][i]).max() / scale)
+        y = cont.isdft(rows).cpu().numpy()
+        assert np.abs(y.astype(np.float64) - g["y"][i]).max() <= 2e-4 * max(np.abs(g["y"][i]).max(), 1e-3), p
+        if p % (2 * m) == 0:
+            # what rank k of an 8-way split computes: a fresh plan primed with the 2m samples before its shard
+            shard = SDFT(m, "hann", 0.5, td="f32", fd="f32")
+            shard.advance(x[p - 2 * m:p])
+            got_s = shard.sdft(x[p:p + keep]).cpu().numpy()
+            worst_s = max(worst_s, np.abs(got_s - g["rows"][i]).max() / scale)
+    assert cont.state()[0] == int(g["final_cursor"])
+    assert worst_c <= 1e-4, worst_c
+    assert worst_s <= 1e-4, worst_s
+    print("config 3 at 2^26 vs the reference: continuous %.3g, halo-primed shards %.3g of full scale" % (worst_c, worst_s))
+
+
 def test_exact_time_sharding_for_double_fd(torch_cuda):
     """Time shards of a DOUBLE frequency-domain plan with a float time domain: the plain halo re-seed
     misses the reference's delta-rounding random walk, the exact variant (one row of m

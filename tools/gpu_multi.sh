@@ -18,6 +18,8 @@ for k in ("value","ms_per_step","roofline","e2e","c3_time_sharded","c3_exact_f64
     print(k, json.dumps(d.get(k))[:1800])
 PY
 tail -5 $OUT/bench_n$N.err
+if [ "$3" != "noref" ]; then
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
     bench.py --impl reference --gpus $N --steps 2 --warmup 1 > $OUT/bench_ref_n$N.json 2> $OUT/bench_ref_n$N.err
 echo "ref exit $?"; cut -c1-300 $OUT/bench_ref_n$N.json
+fi
