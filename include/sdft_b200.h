@@ -214,6 +214,17 @@ SDFT_B200_API int sdft_b200_set_state(sdft_b200_plan_t* plan, size_t channel, si
 SDFT_B200_API double sdft_b200_measure_hbm(int kind, void* device_buffer, size_t bytes, int reps, double* sustained);
 SDFT_B200_API double sdft_b200_measure_dfma(int reps);
 
+/* Shard planners, pure integer arithmetic, the same as sdft_b200/shard.py:
+ * sdft_b200_time_shard: rank `rank` of `world` analyses samples [*begin, *end) of an `nsamples`-sample signal after
+ * priming a fresh plan with samples [*halo_begin, *begin) through *_advance (nothing to prime for rank 0); every
+ * boundary is a multiple of 2*dftsize, where the reference's modulation phase restarts (c/src/sdft/sdft.h:566-576),
+ * so every shard starts at cursor 0.  Trailing ranks may come out empty (*begin == *end) for short signals.
+ * sdft_b200_channel_shard: contiguous channel blocks whose sizes differ by at most one; channels are independent
+ * plans (sdft.h:175-180), nothing is exchanged.  Return 0, or 10002 for world == 0 / rank >= world. */
+SDFT_B200_API int sdft_b200_time_shard(size_t nsamples, size_t world, size_t dftsize, size_t rank, size_t* begin,
+                                       size_t* end, size_t* halo_begin);
+SDFT_B200_API int sdft_b200_channel_shard(size_t channels, size_t world, size_t rank, size_t* begin, size_t* end);
+
 /* Page-locked host memory so that host-pointer calls can DMA straight into the caller's buffer. */
 SDFT_B200_API void* sdft_b200_host_alloc(size_t bytes);
 SDFT_B200_API void sdft_b200_host_free(void* ptr);

@@ -55,6 +55,8 @@ UNTYPED = {
     "sdft_b200_set_state": (_I, [_P, _SZ, _SZ, _P, _P]),
     "sdft_b200_measure_hbm": (_D, [_I, _P, _SZ, _I, ctypes.POINTER(ctypes.c_double)]),
     "sdft_b200_measure_dfma": (_D, [_I]),
+    "sdft_b200_time_shard": (_I, [_SZ, _SZ, _SZ, _SZ] + [ctypes.POINTER(ctypes.c_size_t)] * 3),
+    "sdft_b200_channel_shard": (_I, [_SZ, _SZ, _SZ] + [ctypes.POINTER(ctypes.c_size_t)] * 2),
     "sdft_b200_host_alloc": (_P, [_SZ]),
     "sdft_b200_host_free": (_V, [_P]),
     "sdft_b200_version": (ctypes.c_char_p, []),

@@ -408,6 +408,38 @@ extern "C" double sdft_b200_measure_dfma(int reps)
   return ok ? best : 0.0;
 }
 
+/* shard planners for C / C++ callers: the same integer arithmetic as sdft_b200/shard.py (time_shards,
+ * channel_shards); no device involved */
+extern "C" int sdft_b200_time_shard(size_t nsamples, size_t world, size_t dftsize, size_t rank, size_t* begin, size_t* end,
+                                    size_t* halo_begin)
+{
+  if (world == 0 || dftsize == 0 || rank >= world) return SDFT_B200_ERR_ARG;
+  const size_t period = 2 * dftsize;
+  const size_t periods = (nsamples + period - 1) / period;
+  const size_t base = periods / world, extra = periods % world;
+  size_t b = 0, e = 0;
+  for (size_t r = 0; r <= rank; ++r)
+  {
+    b = e;
+    e = b + (base + (r < extra ? 1 : 0)) * period;
+    if (e > nsamples) e = nsamples;
+  }
+  if (begin) *begin = b;
+  if (end) *end = e;
+  if (halo_begin) *halo_begin = b > period ? b - period : 0;
+  return 0;
+}
+
+extern "C" int sdft_b200_channel_shard(size_t channels, size_t world, size_t rank, size_t* begin, size_t* end)
+{
+  if (world == 0 || rank >= world) return SDFT_B200_ERR_ARG;
+  const size_t base = channels / world, extra = channels % world;
+  const size_t b = rank * base + (rank < extra ? rank : extra);
+  if (begin) *begin = b;
+  if (end) *end = b + base + (rank < extra ? 1 : 0);
+  return 0;
+}
+
 extern "C" void* sdft_b200_host_alloc(size_t bytes)
 {
   void* ptr = nullptr;

@@ -109,3 +109,28 @@ def test_gather_increments_with_gloo(tmp_path):
         rng = np.random.default_rng(r)
         want = (rng.uniform(-1, 1, 19) + 1j * rng.uniform(-1, 1, 19)).astype(np.complex128)
         assert np.array_equal(got[r], want)
+
+
+def test_c_abi_planners_agree_with_python():
+    """sdft_b200_time_shard / sdft_b200_channel_shard (for C and C++ callers) are the same arithmetic as the
+    Python planners; pure host functions, no device needed."""
+    import ctypes
+    import random
+    from sdft_b200 import _lib
+    from sdft_b200.shard import channel_shards, time_shards
+    lib = _lib.load()
+    rnd = random.Random(7)
+    sz = ctypes.c_size_t
+    for _ in range(300):
+        n, world, m = rnd.randrange(0, 1 << 20), rnd.randrange(1, 17), rnd.choice([1, 3, 37, 512, 1000, 2048])
+        for s in time_shards(n, world, m):
+            b, e, h = sz(), sz(), sz()
+            assert lib.sdft_b200_time_shard(n, world, m, s.rank, ctypes.byref(b), ctypes.byref(e), ctypes.byref(h)) == 0
+            assert (b.value, e.value, h.value) == (s.begin, s.end, s.halo_begin)
+        ch = rnd.randrange(0, 600)
+        for r, (lo, hi) in enumerate(channel_shards(ch, world)):
+            b, e = sz(), sz()
+            assert lib.sdft_b200_channel_shard(ch, world, r, ctypes.byref(b), ctypes.byref(e)) == 0
+            assert (b.value, e.value) == (lo, hi)
+    assert lib.sdft_b200_time_shard(100, 0, 8, 0, None, None, None) != 0
+    assert lib.sdft_b200_channel_shard(8, 2, 2, None, None) != 0
