@@ -99,15 +99,18 @@ struct EmitLane
 
   /* geometry of lane `lane` of warp-group `group`: first cell index (signed: the float halo reaches
    * below cell 0) and which of its cells are stored */
-  __device__ __forceinline__ int setup(unsigned group, unsigned lane, unsigned m, unsigned roi_first, unsigned roi_end)
+  __device__ __forceinline__ int setup(unsigned group, unsigned lane, unsigned m, unsigned roi_first, unsigned roi_end,
+                                       unsigned bin_base, unsigned bin_end)
   {
-    const int e0 = (int)(group * G::SPAN) + 2 - G::HALO + (int)(lane * G::CPL);
+    /* this launch covers bins [bin_base, bin_end) -- all of them, unless the call is split into a wide body and
+     * a narrow tail (sdft_launch.hpp) */
+    const int e0 = (int)(bin_base + group * G::SPAN) + 2 - G::HALO + (int)(lane * G::CPL);
 #pragma unroll
     for (int b = 0; b < G::CPL; ++b)
     {
       const int slot = (int)lane * G::CPL + b;
       const int e = e0 + b;
-      ok[b] = (slot >= G::HALO) && (slot < G::WC - G::HALO) && (e >= 2) && (e < (int)m + 2) &&
+      ok[b] = (slot >= G::HALO) && (slot < G::WC - G::HALO) && (e >= 2) && (e < (int)m + 2) && (e < (int)bin_end + 2) &&
               (e >= (int)roi_first + 2) && (e < (int)roi_end + 2);      // bins outside the region of interest are not stored
     }
     return e0;

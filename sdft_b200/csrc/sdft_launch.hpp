@@ -181,129 +181,190 @@ unsigned scan_warps_for(const Plan* p, unsigned chunk, unsigned nchunks, int geo
   return w;
 }
 
-/* production path: the single-pass chained scan/emit kernel (deltas and history are its prologue) */
+/* bins per warp-wide group of a geometry (the halo on either side excluded) */
+unsigned span_of(const Plan* p, int geo, bool no_halo)
+{
+  unsigned wc, halo;
+  if (p->fd == kF32)
+  {
+    wc = geo == GEO_WIDE ? (unsigned)Geo<float, GEO_WIDE>::WC : (unsigned)Geo<float, GEO_NARROW>::WC;
+    halo = (unsigned)Geo<float, GEO_WIDE>::GROUP;
+  }
+  else
+  {
+    wc = geo == GEO_WIDE ? (unsigned)Geo<double, GEO_WIDE>::WC : (unsigned)Geo<double, GEO_NARROW>::WC;
+    halo = (unsigned)Geo<double, GEO_WIDE>::GROUP;
+  }
+  if (p->window == 0 || no_halo) halo = 0;
+  return wc - 2 * halo;
+}
+
+/* one launch of the scan kernel over the bins [bin_base, bin_end) of a call */
+struct ScanPart
+{
+  int geo;
+  unsigned bin_base, bin_end, groups;
+  unsigned slot_id;
+  bool roll_hist;      // writes the next history (the first part of a call)
+  bool last;           // counts the call as completed (the last part of a call)
+};
+
+/* production path: the single-pass chained scan/emit kernel (deltas and history are its prologue).
+ *
+ * A call is ONE launch, except: float rows whose last wide warp group would be mostly empty (m = 2048: the 9th
+ * group holds 64 of its 248 bins and still issues a full warp's instructions -- the float kernel is bound by
+ * FP32 issue, so that is 8 % of the time).  Such a call is split by BINS into a wide body over the full groups
+ * and a narrow tail launch over the remaining bins (half the instructions per step).  Bins are independent
+ * (every group has its own carry chain), so the two launches share nothing but the samples, the state buffers
+ * (each writes the accumulators of the bins it owns) and the hand-over counters. */
 template <typename T, typename F>
 bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride, F* part = nullptr,
                       const F* syn_ab = nullptr, bool syn_unit = false, bool allow_flow = false)
 {
   const unsigned m = (unsigned)p->m;
   const unsigned ch = (unsigned)p->channels;
-  const int geo = choose_geo(p, n);
-  const unsigned chunk = choose_chunk(p, n, geo);
-  const Schedule sched = make_schedule(p->cursor, n, m, chunk);
-  const unsigned groups = groups_for(p, geo, part != nullptr);
-  const size_t wc = (geo == GEO_NARROW) ? (size_t)Geo<F, GEO_NARROW>::WC : (size_t)Geo<F, GEO_WIDE>::WC;
-  const unsigned warps = scan_warps_for(p, chunk, sched.nchunks, geo);
-  const unsigned nblocks = (sched.nchunks + warps - 1) / warps;
-  const size_t items = (size_t)ch * nblocks * groups;
-  if (items >= (1ull << 31))
-  {
-    plan_fail(p, SDFT_B200_ERR_ARG, "analysis: call too large for one launch", __FILE__, __LINE__);
-    return false;
-  }
-
-  /* Streaming (sdft_b200_set_streaming, depth D > 1): a call that produces rows or only updates the state, reads
-   * its samples from device memory and needs little scratch may overlap its predecessors (flow = 1: no wait at
-   * the top of the kernel, hand-over through counters, see sdft_scan.cuh "Between calls").  Call number s takes
-   * scratch slot s % D and first waits until s - D + 1 calls have completed, i.e. until the previous user of its
-   * slot is through: at most D calls are in flight, and the state rings (D + 1 entries, entry s % (D + 1)) never
-   * have a writer and a reader of different calls on one entry.  Everything else (fused round trips: their
-   * finish kernel sits between the scan kernels anyway; calls with large scratch; the default depth 1) is serial:
-   * it waits for all earlier work at the top of the kernel and uses the extra slot D. */
   const unsigned depth = p->stream_depth;
-  const size_t scratch_bytes = 2 * items * wc * sizeof(cx<F>);
+  const int geo = choose_geo(p, n);
+  const double work = (double)n * (double)m * (double)ch;
   /* overlap pays where a call's fixed latencies (ticket, first look-back, drain: ~10 us) are a visible share of
    * it: up to ~2^28 bin-updates (0.7 ms).  Longer calls gain nothing and one shape was measured slower
    * (profiles/r02_v1_mid_sweep.md: m = 4096 float, 2^18 samples per call), so they stay serial. */
-  const bool short_call = (double)n * (double)m * (double)ch <= 268435456.0;
-  const unsigned flow = (depth > 1 && allow_flow && !part && short_call && scratch_bytes <= ((size_t)32 << 20)) ? 1u : 0u;
-  const unsigned seq = p->calls_issued++;
-  const unsigned slot_id = flow ? seq % depth : depth;
-  Plan::Slot& slot = p->slots[slot_id];
-  if (!reserve(p, slot.prefix, items * wc * sizeof(cx<F>))) return false;
-  if (!reserve(p, slot.chain_totals, items * wc * sizeof(cx<F>))) return false;
-  const size_t flags_before = slot.flags.bytes;
-  if (!reserve(p, slot.flags, items * sizeof(unsigned))) return false;
-  if (slot.flags.bytes != flags_before || slot.epoch >= 0x7ffffff0u)
-  {
-    CU_TRY(p, cudaMemsetAsync(slot.flags.ptr, 0, slot.flags.bytes, p->stream));   // a stream operation: serializes
-    slot.epoch = 0;
-  }
-  slot.epoch++;
-  const size_t ring = p->history.size();
+  const bool may_flow = depth > 1 && allow_flow && !part && work <= 268435456.0;
 
-  ChainArgs<F> a;
-  a.sched = sched;
-  a.samples = x;
-  a.sample_stride = x_stride;
-  a.hist_old = p->history[p->state_sel];
-  a.hist_new = p->history[(p->state_sel + 1) % ring];
-  a.td_double = (type_id<T>::value == kF64) ? 1 : 0;
-  a.scale = (F)p->prescale;
-  a.tw_ext = (const cx<F>*)p->tw_ext;
-  a.phase = phase_source<F>(p);
-  a.acc_in = (const cx<F>*)p->acc_state[p->state_sel];
-  a.acc_out = (cx<F>*)p->acc_state[(p->state_sel + 1) % ring];
-  a.prefix = (cx<F>*)slot.prefix.ptr;
-  a.totals = (cx<F>*)slot.chain_totals.ptr;
-  a.flags = (unsigned*)slot.flags.ptr;
-  a.error = p->control;
-  a.handover = depth > 1 ? 1u : 0u;
-  a.completed = depth > 1 ? p->control + 1 : nullptr;
-  a.completed_target = (seq >= depth) ? seq - depth + 1 : 0;
-  a.ticket = p->control + 2 + 4 * slot_id;
-  a.sync = p->control + 3 + 4 * slot_id;
-  a.finished = p->control + 5 + 4 * slot_id;
-  a.prev_sync = p->control + 3 + 4 * p->prev_slot;
-  a.prev_hist_target = p->slots[p->prev_slot].hist_total;
-  a.prev_acc_target = p->slots[p->prev_slot].acc_total;
-  a.flow = flow;
-  a.epoch = slot.epoch;
-  a.total_blocks = (unsigned)items;
-  a.nblocks = nblocks;
-  a.channels = ch;
-  a.m = m;
-  a.cells = (unsigned)p->cells;
-  a.out = out;
-  a.out_channel_stride = out_stride;
-  a.roi_first = (unsigned)p->roi_first;
-  a.roi_count = (unsigned)row_bins(p);
-  a.syn_ab = syn_ab;
-  a.part = part;
-  a.groups = groups;
-  a.stage_rows = (geo == GEO_NARROW) ? scan_stage_rows<F, GEO_NARROW>(warps, chunk) : scan_stage_rows<F, GEO_WIDE>(warps, chunk);
-  a.win = make_window_const<F>(p->m, p->window);   // sdft.h:422, :371
-  a.trace = nullptr;
+  ScanPart parts[2];
+  int nparts = 1;
+  parts[0] = { geo, 0u, m, groups_for(p, geo, part != nullptr), 0u, true, true };
+  if (geo == GEO_WIDE && p->fd == kF32 && p->mode == MODE_FAST && !part && !may_flow && p->window != 0 && p->forced_geo < 0 &&
+      work >= 67108864.0 && !getenv("SDFT_B200_NO_SPLIT"))
+  {
+    const unsigned span_w = span_of(p, GEO_WIDE, false), span_n = span_of(p, GEO_NARROW, false);
+    const unsigned full = m / span_w, rest = m - full * span_w;
+    if (full >= 1 && full <= 11 && rest > 0 && rest <= span_n)
+    {
+      parts[0] = { GEO_WIDE, 0u, full * span_w, full, 0u, true, false };
+      parts[1] = { GEO_NARROW, full * span_w, m, 1u, 0u, false, true };
+      nparts = 2;
+    }
+  }
+
+  const unsigned seq = p->calls_issued++;
+  const size_t ring = p->history.size();
+  const unsigned prev_slot = p->prev_slot;
+  unsigned flow = 0, first_slot = 0, hist_signals = 0, acc_signals = 0;
+  if (part || out) prof_mark(p, 0);
+  for (int q = 0; q < nparts; ++q)
+  {
+    ScanPart& sp = parts[q];
+    const unsigned chunk = choose_chunk(p, n, sp.geo);
+    const Schedule sched = make_schedule(p->cursor, n, m, chunk);
+    const size_t wc = (sp.geo == GEO_NARROW) ? (size_t)Geo<F, GEO_NARROW>::WC : (size_t)Geo<F, GEO_WIDE>::WC;
+    const unsigned warps = scan_warps_for(p, chunk, sched.nchunks, sp.geo);
+    const unsigned nblocks = (sched.nchunks + warps - 1) / warps;
+    const size_t items = (size_t)ch * nblocks * sp.groups;
+    if (items >= (1ull << 31))
+    {
+      plan_fail(p, SDFT_B200_ERR_ARG, "analysis: call too large for one launch", __FILE__, __LINE__);
+      return false;
+    }
+    /* Streaming (sdft_b200_set_streaming, depth D > 1): a call that produces rows or only updates the state,
+     * reads its samples from device memory, is short and needs little scratch may overlap its predecessors
+     * (flow = 1: no wait at the top of the kernel, hand-over through counters, see sdft_scan.cuh "Between
+     * calls").  Call number s takes scratch slot s % D and first waits until s - D + 1 calls have completed,
+     * i.e. until the previous user of its slot is through: at most D calls are in flight, and the state rings
+     * (D + 1 entries) never have a writer and a reader of different calls on one entry.  Everything else (fused
+     * round trips: their finish kernel sits between the scan kernels anyway; long calls; the default depth 1)
+     * is serial: it waits for all earlier work at the top of the kernel and uses the extra slots D (and D + 1
+     * for the tail launch of a split call). */
+    const size_t scratch_bytes = 2 * items * wc * sizeof(cx<F>);
+    if (q == 0) flow = (may_flow && scratch_bytes <= ((size_t)32 << 20)) ? 1u : 0u;
+    sp.slot_id = flow ? seq % depth : depth + (unsigned)q;
+    if (q == 0) first_slot = sp.slot_id;
+    Plan::Slot& slot = p->slots[sp.slot_id];
+    if (!reserve(p, slot.prefix, items * wc * sizeof(cx<F>))) return false;
+    if (!reserve(p, slot.chain_totals, items * wc * sizeof(cx<F>))) return false;
+    const size_t flags_before = slot.flags.bytes;
+    if (!reserve(p, slot.flags, items * sizeof(unsigned))) return false;
+    if (slot.flags.bytes != flags_before || slot.epoch >= 0x7ffffff0u)
+    {
+      CU_TRY(p, cudaMemsetAsync(slot.flags.ptr, 0, slot.flags.bytes, p->stream));   // a stream operation: serializes
+      slot.epoch = 0;
+    }
+    slot.epoch++;
+
+    ChainArgs<F> a;
+    a.sched = sched;
+    a.samples = x;
+    a.sample_stride = x_stride;
+    a.hist_old = p->history[p->state_sel];
+    a.hist_new = p->history[(p->state_sel + 1) % ring];
+    a.td_double = (type_id<T>::value == kF64) ? 1 : 0;
+    a.scale = (F)p->prescale;
+    a.tw_ext = (const cx<F>*)p->tw_ext;
+    a.phase = phase_source<F>(p);
+    a.acc_in = (const cx<F>*)p->acc_state[p->state_sel];
+    a.acc_out = (cx<F>*)p->acc_state[(p->state_sel + 1) % ring];
+    a.prefix = (cx<F>*)slot.prefix.ptr;
+    a.totals = (cx<F>*)slot.chain_totals.ptr;
+    a.flags = (unsigned*)slot.flags.ptr;
+    a.error = p->control;
+    a.handover = depth > 1 ? 1u : 0u;
+    a.completed = (depth > 1 && sp.last) ? p->control + 1 : nullptr;
+    a.completed_target = (seq >= depth) ? seq - depth + 1 : 0;
+    a.ticket = p->control + 2 + 4 * sp.slot_id;
+    a.sync = p->control + 3 + 4 * first_slot;          // both launches of a split call hand over through one pair of counters
+    a.finished = p->control + 5 + 4 * sp.slot_id;
+    a.prev_sync = p->control + 3 + 4 * prev_slot;
+    a.prev_hist_target = p->slots[prev_slot].hist_total;
+    a.prev_acc_target = p->slots[prev_slot].acc_total;
+    a.flow = flow;
+    a.epoch = slot.epoch;
+    a.total_blocks = (unsigned)items;
+    a.nblocks = nblocks;
+    a.channels = ch;
+    a.m = m;
+    a.cells = (unsigned)p->cells;
+    a.out = out;
+    a.out_channel_stride = out_stride;
+    a.roi_first = (unsigned)p->roi_first;
+    a.roi_count = (unsigned)row_bins(p);
+    a.syn_ab = syn_ab;
+    a.part = part;
+    a.groups = sp.groups;
+    a.bin_base = sp.bin_base;
+    a.bin_end = sp.bin_end;
+    a.roll_hist = sp.roll_hist ? 1u : 0u;
+    a.stage_rows = (sp.geo == GEO_NARROW) ? scan_stage_rows<F, GEO_NARROW>(warps, chunk) : scan_stage_rows<F, GEO_WIDE>(warps, chunk);
+    a.win = make_window_const<F>(p->m, p->window);   // sdft.h:422, :371
+    a.trace = nullptr;
 #if defined(SDFT_B200_TRACE)
-  if (reserve(p, p->trace, items * 8 * sizeof(unsigned long long)))
-  {
-    a.trace = (unsigned long long*)p->trace.ptr;
-    p->trace_items = items;
-  }
+    if (reserve(p, p->trace, items * 8 * sizeof(unsigned long long)))
+    {
+      a.trace = (unsigned long long*)p->trace.ptr;
+      p->trace_items = items;
+    }
 #endif
-  if (part)
-  {
-    prof_mark(p, 0);
-    if (syn_unit) launch_chain<F, EMIT_SYNTH_UNIT>(p, a, false, warps, geo);   // all imaginary-part weights are zero
-    else launch_chain<F, EMIT_SYNTH>(p, a, false, warps, geo);
-    prof_mark(p, 0);
+    if (part)
+    {
+      if (syn_unit) launch_chain<F, EMIT_SYNTH_UNIT>(p, a, false, warps, sp.geo);   // all imaginary-part weights are zero
+      else launch_chain<F, EMIT_SYNTH>(p, a, false, warps, sp.geo);
+    }
+    else if (out)
+    {
+      launch_chain<F, EMIT_ROWS>(p, a, can_vectorize<F>(p, out, out_stride), warps, sp.geo);
+    }
+    else
+    {
+      launch_chain<F, EMIT_NONE>(p, a, false, warps, sp.geo);
+    }
+    CU_TRY(p, cudaGetLastError());
+    if (sp.roll_hist) hist_signals += nblocks * ch;
+    acc_signals += sp.groups * ch;
   }
-  else if (out)
-  {
-    const bool vec = can_vectorize<F>(p, out, out_stride);
-    prof_mark(p, 0);
-    launch_chain<F, EMIT_ROWS>(p, a, vec, warps, geo);
-    prof_mark(p, 0);
-  }
-  else
-  {
-    launch_chain<F, EMIT_NONE>(p, a, false, warps, geo);
-  }
-  CU_TRY(p, cudaGetLastError());
+  if (part || out) prof_mark(p, 0);
   /* what this call will have handed over once its group-0 CTAs / last block items are through */
-  slot.hist_total += nblocks * ch;
-  slot.acc_total += groups * ch;
-  p->prev_slot = slot_id;
+  p->slots[first_slot].hist_total += hist_signals;
+  p->slots[first_slot].acc_total += acc_signals;
+  p->prev_slot = first_slot;
   p->state_sel = (p->state_sel + 1) % ring;
   p->cursor = (size_t)((p->cursor + n) % (2 * (size_t)m));
   return true;

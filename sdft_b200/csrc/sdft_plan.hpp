@@ -83,7 +83,8 @@ struct sdft_b200_plan
     unsigned epoch = 0;
     unsigned hist_total = 0, acc_total = 0;
   };
-  std::vector<Slot> slots;       // stream_depth slots for streaming calls (call seq % depth) + one for serial calls
+  std::vector<Slot> slots;       // stream_depth slots for streaming calls (call seq % depth), one for serial calls, one for
+                                 // the narrow tail launch of a split call (sdft_launch.hpp)
   unsigned* control = nullptr;   // [0] timeout flag, [1] completed calls, then per slot: ticket, history, accumulators, finished
   unsigned stream_depth = 1;     // calls that may be in flight at once (1: serial; sdft_b200_set_streaming)
   unsigned calls_issued = 0;     // analysis launches since the rings were (re)allocated; the device counts them out again
@@ -290,11 +291,11 @@ bool plan_rings(Plan* p, unsigned depth)
   for (Plan::Slot& s : p->slots)
     for (Buffer* b : { &s.prefix, &s.chain_totals, &s.flags })
       if (b->ptr) cudaFree(b->ptr);
-  p->slots.assign(depth + 1, Plan::Slot());
+  p->slots.assign(depth + 2, Plan::Slot());      // streaming slots, the serial slot, the tail slot of split calls
   if (p->control) cudaFree(p->control);
   p->control = nullptr;
-  CU_TRY(p, cudaMalloc(&p->control, (2 + 4 * ((size_t)depth + 1)) * sizeof(unsigned)));
-  CU_TRY(p, cudaMemset(p->control, 0, (2 + 4 * ((size_t)depth + 1)) * sizeof(unsigned)));
+  CU_TRY(p, cudaMalloc(&p->control, (2 + 4 * ((size_t)depth + 2)) * sizeof(unsigned)));
+  CU_TRY(p, cudaMemset(p->control, 0, (2 + 4 * ((size_t)depth + 2)) * sizeof(unsigned)));
   p->stream_depth = depth;
   p->calls_issued = 0;
   p->prev_slot = 0;

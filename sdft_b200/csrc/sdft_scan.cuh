@@ -111,6 +111,9 @@ template <typename F> struct ChainArgs
   const F* syn_ab;         // (m, 2) synthesis weights of Re / Im of every bin with the window folded in, EMIT_SYNTH only
   F* part;                 // (channels, groups, n) per-group partial sums of the fused synthesis
   unsigned groups;
+  unsigned bin_base;       // this launch covers bins [bin_base, bin_end) in `groups` warp-wide groups: everything,
+  unsigned bin_end;        // or the wide body / the narrow tail of a split call
+  unsigned roll_hist;      // 1: the CTAs of group 0 write the next history (exactly one launch of a call does)
   unsigned stage_rows;     // rows of look-back staging in shared memory (scan_stage_rows)
   WindowConst<F> win;
   unsigned long long* trace;   // -DSDFT_B200_TRACE builds only: 8 %globaltimer stamps per CTA, else unused
@@ -489,7 +492,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
       const unsigned g0 = (t - jb0 * per) % a.groups;
       const unsigned first = jb0 * (blockDim.x >> 5);
       const bool reads_hist = (first < a.sched.nchunks && chunk_span(a.sched, first).t0 < a.sched.period) ||
-                              (g0 == 0 && a.sched.n < a.sched.period);
+                              (g0 == 0 && a.roll_hist && a.sched.n < a.sched.period);
       if (reads_hist) wait_counter(a.prev_sync, a.prev_hist_target, a.error);
     }
   }
@@ -518,7 +521,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
     else chunk_deltas<float, F>(a, ch, cs, sdelta, lane);
     if (lane < 2) sdelta[cs.len + lane] = (F)0;
   }
-  if (group == 0)
+  if (group == 0 && a.roll_hist)
   {
     if (a.td_double) roll_history<double, F>(a, ch, jb);
     else roll_history<float, F>(a, ch, jb);
@@ -535,7 +538,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   EmitLane<F, WINDOW, VEC, GEO> L;
   const bool synth = (EMIT == EMIT_SYNTH_UNIT || EMIT == EMIT_SYNTH);       // the fused synthesis always sees every bin
   const unsigned roi_first = synth ? 0u : a.roi_first, roi_end = synth ? a.m : a.roi_first + a.roi_count;
-  const int e0 = L.setup(group, lane, a.m, roi_first, roi_end);
+  const int e0 = L.setup(group, lane, a.m, roi_first, roi_end, a.bin_base, a.bin_end);
   bool live[G::CPL];
   cx<F> zero;
   zero.r = (F)0; zero.i = (F)0;
@@ -715,9 +718,13 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
       }
       else
       {
+        /* every cell is written by the launch that OWNS its bin (halo cells are recomputed, not owned): the two
+         * launches of a split call add their carries up in different orders */
+        const int own_lo = a.bin_base == 0 ? 0 : (int)a.bin_base + 2;
+        const int own_hi = a.bin_end == a.m ? (int)a.cells : (int)a.bin_end + 2;
 #pragma unroll
         for (int b = 0; b < G::CPL; ++b)
-          if (live[b]) ao[e0 + b] = agg[b];
+          if (live[b] && e0 + b >= own_lo && e0 + b < own_hi) ao[e0 + b] = agg[b];
       }
       if (a.handover)
       {
@@ -753,7 +760,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   if (EMIT == EMIT_ROWS)
   {
     /* groups without a bin inside the region of interest have done their share (the carries): no rows */
-    if (group * (unsigned)G::SPAN >= roi_end || (group + 1u) * (unsigned)G::SPAN <= roi_first)
+    if (a.bin_base + group * (unsigned)G::SPAN >= roi_end || a.bin_base + (group + 1u) * (unsigned)G::SPAN <= roi_first)
     {
       warp_finish(&s_warps_done, nwarps, a.finished, a.total_blocks, a.completed);
       return;

@@ -245,6 +245,48 @@ def test_large_and_odd_dft_sizes(SDFT, m, fd):
     assert g.state()[0] == o.state()[0]
 
 
+@pytest.mark.parametrize("m,window", [(2048, "hann"), (1024, "blackman"), (2000, "hamming")])
+def test_float_calls_split_into_wide_body_and_narrow_tail(SDFT, m, window, monkeypatch):
+    """Long float calls whose last wide warp group would be mostly empty run as two launches over disjoint bin
+    ranges (sdft_launch.hpp: ScanPart): rows, synthesized samples and state against the oracle over several calls,
+    with a state-only call and a region of interest in between, and against the same plan with the split
+    disabled (identical up to the order in which the tail's carries are added)."""
+    import torch
+    from oracle import Oracle
+    n = (1 << 26) // m + 1000
+    rng = np.random.default_rng(seed_of("split", m, window))
+    g = SDFT(m, window, 0.5, td="f32", fd="f32")
+    monkeypatch.setenv("SDFT_B200_NO_SPLIT", "1")
+    one = SDFT(m, window, 0.5, td="f32", fd="f32")
+    monkeypatch.delenv("SDFT_B200_NO_SPLIT")
+    o = Oracle("f32", "f32", m, window, 0.5)
+    launches0 = g.launches
+    for call in range(3):
+        x = rng.uniform(-1, 1, n).astype(np.float32)
+        xt = torch.from_numpy(x).cuda()
+        if call == 1:
+            g.advance(xt); one.advance(xt); o.advance(x)
+            continue
+        got, ref = g.sdft(xt), one.sdft(xt)
+        want = o.sdft(x)
+        assert rel_err(got.cpu().numpy(), want) <= TOL["f32"], (call, rel_err(got.cpu().numpy(), want))
+        assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+        y, yw = g.isdft(got).cpu().numpy(), o.isdft(want)
+        assert np.abs(y.astype(np.float64) - yw).max() <= 2e-4 * max(np.abs(yw).max(), 1e-3)
+    assert g.launches - launches0 == 2 * 3 + 2, "every long call is two scan launches"
+    cg, hg, ag, pg = g.state()
+    co, ho, ao, po = o.state()
+    assert cg == co and np.array_equal(_bits(hg), _bits(ho)) and np.array_equal(_bits(pg), _bits(po))
+    assert rel_err(ag, ao) <= TOL["f32"]
+    # the last bins (the tail launch's) through a region of interest
+    g.set_roi(m - 96, 96)
+    x = rng.uniform(-1, 1, n).astype(np.float32)
+    got = g.sdft(torch.from_numpy(x).cuda()).cpu().numpy()
+    want = o.sdft(x)
+    assert got.shape == (n, 96)
+    assert np.abs(got - want[:, m - 96:]).max() <= TOL["f32"] * np.abs(want).max()
+
+
 @pytest.mark.parametrize("budget_mb,m", [(1, 4096), (0, 1000), (2, 10007)])
 def test_float_phase_table_with_a_coarse_stride(SDFT, budget_mb, m, monkeypatch):
     """The float phase table holds the reference's sequential fiddle recurrence at every `stride`-th cursor
