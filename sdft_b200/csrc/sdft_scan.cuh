@@ -57,8 +57,9 @@ namespace sdftb200
  *          the plan counts completed calls ([completed], bumped by the last CTA of every call), and a
  *          streaming call first makes sure that the call D calls back -- the previous user of its slot --
  *          is among them, which bounds the calls in flight to D (sdft_launch.hpp).
- *      Every thread ends with griddepcontrol.wait: a call completes only after its predecessor has, so work
- *      queued behind the calls in the ordinary way still sees all of them finished.
+ *      On a streaming plan every thread ends with griddepcontrol.wait: a call completes only after its
+ *      predecessor has, so work queued behind the calls in the ordinary way still sees all of them finished
+ *      (a plan that never streams gets the same from the wait at the top of each call).
  * ---------------------------------------------------------------------------------------------- */
 #ifndef SDFT_B200_EMIT_UNROLL
 #define SDFT_B200_EMIT_UNROLL 2        // time steps unrolled in the row loop
@@ -171,10 +172,13 @@ __device__ __forceinline__ void grid_dependency_wait()
 /* last instruction of every warp of the scan kernel: keep the order of completion, then count this warp out; the
  * last warp of the last CTA rearms the slot's counter and bumps the plan's count of completed calls */
 __device__ __forceinline__ void warp_finish(unsigned* s_warps_done, unsigned nwarps, unsigned* finished, unsigned total_blocks,
-                                            unsigned* completed)
+                                            unsigned* completed, unsigned handover)
 {
+  /* a plan that never streams needs none of this: each of its calls waits for its predecessor at the top, so it
+   * cannot complete before it */
+  if (!handover) return;
   grid_dependency_wait();
-  if (!completed) return;       // plan not in streaming mode: nobody counts calls
+  if (!completed) return;       // the body launch of a split call: the tail launch counts the call
   __syncwarp();
   if ((threadIdx.x & 31u) == 0u)
   {
@@ -754,7 +758,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
     }
   }
   SDFT_B200_STAMP(5);   // carries distributed, replay starts
-  if (!valid) { warp_finish(&s_warps_done, nwarps, a.finished, a.total_blocks, a.completed); return; }
+  if (!valid) { warp_finish(&s_warps_done, nwarps, a.finished, a.total_blocks, a.completed, a.handover); return; }
 
   /* ---- phase C: replay from the carry and stream the rows out ---- */
   if (EMIT == EMIT_ROWS)
@@ -762,7 +766,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
     /* groups without a bin inside the region of interest have done their share (the carries): no rows */
     if (a.bin_base + group * (unsigned)G::SPAN >= roi_end || a.bin_base + (group + 1u) * (unsigned)G::SPAN <= roi_first)
     {
-      warp_finish(&s_warps_done, nwarps, a.finished, a.total_blocks, a.completed);
+      warp_finish(&s_warps_done, nwarps, a.finished, a.total_blocks, a.completed, a.handover);
       return;
     }
     const size_t row_stride = a.roi_count;
@@ -872,7 +876,7 @@ SDFT_B200_PRAGMA_UNROLL(SDFT_B200_EMIT_UNROLL)
     }
   }
   SDFT_B200_STAMP(6);   // warp 0 finished its rows
-  warp_finish(&s_warps_done, nwarps, a.finished, a.total_blocks, a.completed);   // completes only after the call before it
+  warp_finish(&s_warps_done, nwarps, a.finished, a.total_blocks, a.completed, a.handover);   // completes only after the call before it
 }
 #undef stot
 

@@ -192,15 +192,17 @@ def test_config3_full_size_against_reference_rows(torch_cuda, golden_dir):
     x = torch.from_numpy(workloads.chirp(n)).cuda()
     scale = float(np.abs(g["rows"]).max())
     cont = SDFT(m, "hann", 0.5, td="f32", fd="f32")
-    pos, worst_c, worst_s = 0, 0.0, 0.0
+    pos, worst_c, worst_s, worst_y = 0, 0.0, 0.0, 0.0
     for i, p in enumerate(probes):
         cont.advance(x[pos:p])
         rows = cont.sdft(x[p:p + keep])
         pos = p + keep
         got = rows.cpu().numpy()
         worst_c = max(worst_c, np.abs(got - g["rows"][i]).max() / scale)
+        # a synthesized sample sums 2048 bins, i.e. 2048 row differences that are each inside the gate: the bar for
+        # samples is the one the 2^20 test uses (1e-3 of full scale; full scale is 1 for this chirp)
         y = cont.isdft(rows).cpu().numpy()
-        assert np.abs(y.astype(np.float64) - g["y"][i]).max() <= 2e-4 * max(np.abs(g["y"][i]).max(), 1e-3), p
+        worst_y = max(worst_y, np.abs(y.astype(np.float64) - g["y"][i]).max())
         if p % (2 * m) == 0:
             # what rank k of an 8-way split computes: a fresh plan primed with the 2m samples before its shard
             shard = SDFT(m, "hann", 0.5, td="f32", fd="f32")
@@ -210,7 +212,9 @@ def test_config3_full_size_against_reference_rows(torch_cuda, golden_dir):
     assert cont.state()[0] == int(g["final_cursor"])
     assert worst_c <= 1e-4, worst_c
     assert worst_s <= 1e-4, worst_s
-    print("config 3 at 2^26 vs the reference: continuous %.3g, halo-primed shards %.3g of full scale" % (worst_c, worst_s))
+    assert worst_y <= 1e-3, worst_y
+    print("config 3 at 2^26 vs the reference: rows continuous %.3g, halo-primed shards %.3g of full scale; samples %.3g"
+          % (worst_c, worst_s, worst_y))
 
 
 def test_exact_time_sharding_for_double_fd(torch_cuda):
