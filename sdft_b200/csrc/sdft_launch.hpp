@@ -235,7 +235,7 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   int nparts = 1;
   parts[0] = { geo, 0u, m, groups_for(p, geo, part != nullptr), 0u, true, true };
   if (geo == GEO_WIDE && p->fd == kF32 && p->mode == MODE_FAST && !part && !may_flow && p->window != 0 && p->forced_geo < 0 &&
-      work >= 67108864.0 && !getenv("SDFT_B200_NO_SPLIT"))
+      work >= 67108864.0 && !p->no_split)
   {
     const unsigned span_w = span_of(p, GEO_WIDE, false), span_n = span_of(p, GEO_NARROW, false);
     const unsigned full = m / span_w, rest = m - full * span_w;
@@ -247,7 +247,7 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
     }
   }
 
-  const unsigned seq = p->calls_issued++;
+  const unsigned long long seq = p->calls_issued++;
   const size_t ring = p->history.size();
   const unsigned prev_slot = p->prev_slot;
   unsigned flow = 0, first_slot = 0, hist_signals = 0, acc_signals = 0;
@@ -277,7 +277,7 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
      * for the tail launch of a split call). */
     const size_t scratch_bytes = 2 * items * wc * sizeof(cx<F>);
     if (q == 0) flow = (may_flow && scratch_bytes <= ((size_t)32 << 20)) ? 1u : 0u;
-    sp.slot_id = flow ? seq % depth : depth + (unsigned)q;
+    sp.slot_id = flow ? (unsigned)(seq % depth) : depth + (unsigned)q;
     if (q == 0) first_slot = sp.slot_id;
     Plan::Slot& slot = p->slots[sp.slot_id];
     if (!reserve(p, slot.prefix, items * wc * sizeof(cx<F>))) return false;
@@ -309,7 +309,8 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
     a.error = p->control;
     a.handover = depth > 1 ? 1u : 0u;
     a.completed = (depth > 1 && sp.last) ? p->control + 1 : nullptr;
-    a.completed_target = (seq >= depth) ? seq - depth + 1 : 0;
+    a.completed_target = (unsigned)(seq - depth + 1);      // modulo 2^32, compared wrap-safe; no wait for the first calls:
+    a.wait_completed = (seq >= depth) ? 1u : 0u;
     a.ticket = p->control + 2 + 4 * sp.slot_id;
     a.sync = p->control + 3 + 4 * first_slot;          // both launches of a split call hand over through one pair of counters
     a.finished = p->control + 5 + 4 * sp.slot_id;

@@ -41,6 +41,7 @@ struct sdft_b200_plan
   int forced_geo = -1;           // SDFT_B200_GEO=wide|narrow: warp geometry (default: per call, choose_geo)
   bool driver_pageable = false;  // SDFT_B200_PAGEABLE=driver: leave pageable buffers to cudaMemcpy (for comparison)
   bool pdl = true;               // SDFT_B200_PDL=0: plain stream-ordered launches
+  bool no_split = false;         // SDFT_B200_NO_SPLIT=1: never split a float call into wide body + narrow tail (for comparison)
   size_t tile_bytes = 0;
   unsigned long long launches = 0;
 
@@ -87,7 +88,8 @@ struct sdft_b200_plan
                                  // the narrow tail launch of a split call (sdft_launch.hpp)
   unsigned* control = nullptr;   // [0] timeout flag, [1] completed calls, then per slot: ticket, history, accumulators, finished
   unsigned stream_depth = 1;     // calls that may be in flight at once (1: serial; sdft_b200_set_streaming)
-  unsigned calls_issued = 0;     // analysis launches since the rings were (re)allocated; the device counts them out again
+  unsigned long long calls_issued = 0;   // analysis calls since the rings were (re)allocated; the device counts them out
+                                         // again modulo 2^32 (an endless stream gets there: 8 hours of 4096-sample calls)
   unsigned prev_slot = 0;        // slot of the previous call
 
   /* optional CUDA-event timing of the dominant kernels (bench.py roofline): [0] analysis emit, [1] synthesis */
@@ -470,6 +472,7 @@ Plan* plan_create(size_t m, int window, double latency, size_t channels)
     const char* pg = getenv("SDFT_B200_PAGEABLE");
     p->driver_pageable = pg && !strcmp(pg, "driver");
     p->pdl = env_size("SDFT_B200_PDL", 1) != 0;
+    p->no_split = env_size("SDFT_B200_NO_SPLIT", 0) != 0;
     const char* ge = getenv("SDFT_B200_GEO");
     if (ge && !strcmp(ge, "wide")) p->forced_geo = GEO_WIDE;
     if (ge && !strcmp(ge, "narrow")) p->forced_geo = GEO_NARROW;

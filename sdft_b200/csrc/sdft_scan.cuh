@@ -98,7 +98,8 @@ template <typename F> struct ChainArgs
                            // poll them); 0: every call on the plan is serial, nobody ever looks
   unsigned* finished;      // CTAs of this call that are through (this call's slot); the last one rearms it and ...
   unsigned* completed;     // ... bumps the plan's count of completed calls (calls complete in order)
-  unsigned completed_target;   // streaming: calls that must have completed before this one may touch its slot
+  unsigned completed_target;   // streaming: calls that must have completed before this one may touch its slot (mod 2^32)
+  unsigned wait_completed;     // 0 for the first `depth` calls on fresh rings: nothing to wait for
   unsigned epoch;
   unsigned total_blocks;   // nblocks * channels * groups
   unsigned nblocks;        // block items per chain: ceil(nchunks / warps per CTA)
@@ -483,7 +484,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const Cha
   if (threadIdx.x == 0)
   {
     s_warps_done = 0;
-    if (a.flow) wait_counter(a.completed, a.completed_target, a.error);   // the slot's previous user is through
+    if (a.flow && a.wait_completed) wait_counter(a.completed, a.completed_target, a.error);   // the slot's previous user is through
     const unsigned t = atomicAdd(a.ticket, 1u);
     if (t == a.total_blocks - 1) *a.ticket = 0;   // last ticket of the launch: rearm the slot for its next call
     s_ticket = t;

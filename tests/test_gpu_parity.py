@@ -253,7 +253,7 @@ def test_float_calls_split_into_wide_body_and_narrow_tail(SDFT, m, window, monke
     disabled (identical up to the order in which the tail's carries are added)."""
     import torch
     from oracle import Oracle
-    n = (1 << 26) // m + 1000
+    n = 1700000 // (-(-m // 248)) + 1000          # enough warp-steps for the wide geometry (choose_geo), >= 2^26 bin-updates
     rng = np.random.default_rng(seed_of("split", m, window))
     g = SDFT(m, window, 0.5, td="f32", fd="f32")
     monkeypatch.setenv("SDFT_B200_NO_SPLIT", "1")
