@@ -21,8 +21,9 @@ void prof_mark(Plan* p, int which)
   p->prof_events[which].push_back(e);
 }
 
-/* warp-wide groups of bins the plan's m bins are cut into, for either warp geometry */
-unsigned groups_for(const Plan* p, int geo = GEO_WIDE, bool no_halo = false)
+/* bins per warp-wide group of a geometry: the warp's cells minus the halo it recomputes on either side (none for
+ * the boxcar window, and none in the fused synthesis, which folds the window into its weights: no taps) */
+unsigned span_of(const Plan* p, int geo, bool no_halo)
 {
   unsigned wc, halo;
   if (p->fd == kF32)
@@ -35,8 +36,14 @@ unsigned groups_for(const Plan* p, int geo = GEO_WIDE, bool no_halo = false)
     wc = geo == GEO_WIDE ? (unsigned)Geo<double, GEO_WIDE>::WC : (unsigned)Geo<double, GEO_NARROW>::WC;
     halo = (unsigned)Geo<double, GEO_WIDE>::GROUP;
   }
-  if (p->window == 0 || no_halo) halo = 0;    // the fused synthesis folds the window into its weights: no taps, no halo
-  const unsigned span = wc - 2 * halo;
+  if (p->window == 0 || no_halo) halo = 0;
+  return wc - 2 * halo;
+}
+
+/* warp-wide groups of bins the plan's m bins are cut into, for either warp geometry */
+unsigned groups_for(const Plan* p, int geo = GEO_WIDE, bool no_halo = false)
+{
+  const unsigned span = span_of(p, geo, no_halo);
   return (unsigned)((p->m + span - 1) / span);
 }
 
@@ -64,19 +71,7 @@ bool can_vectorize(const Plan* p, const void* out, size_t out_stride)
   return (row_bins(p) % g == 0) && (p->roi_first % g == 0) && (((uintptr_t)out) % 32 == 0) && (out_stride % g == 0);
 }
 
-unsigned choose_chunk_free(const Plan* p, size_t n, int geo);
-
-/* chunk length of a call: the measured optimum, rounded up to a multiple of the float phase table's stride so
- * that every chunk but the first of a call starts on a table row (no rotations) */
-unsigned choose_chunk(const Plan* p, size_t n, int geo)
-{
-  unsigned c = choose_chunk_free(p, n, geo);
-  const unsigned s = p->f0_stride;
-  c = ((c + s - 1) / s) * s;
-  if (c > (unsigned)kMaxChunk) c = kMaxChunk;
-  return c;
-}
-
+/* the measured optimum for a call (any multiple of 32) */
 unsigned choose_chunk_free(const Plan* p, size_t n, int geo)
 {
   if (p->forced_chunk)
@@ -95,7 +90,7 @@ unsigned choose_chunk_free(const Plan* p, size_t n, int geo)
     /* profiles/r01_geo_sweep.md: narrow warps like longer chunks earlier, but never so long that a chain
      * has fewer than 16 chunks.  Streaming calls overlap their neighbours, so the latency of a chunk's serial
      * steps hides behind other calls' work and the per-chunk overheads decide: 128 from the start
-     * (profiles/r02_stream_sweep.md: 6.7 us instead of 7.3-7.8 per 4096-sample call at m = 512) */
+     * (profiles/r02_v1_stream_sweep.md: 6.7 us instead of 7.3-7.8 per 4096-sample call at m = 512) */
     unsigned c = (u < 16384.0) ? 32u : ((u < 30.0e3) ? 64u : 128u);
     if (p->stream_depth > 1 && c < 128u) c = 128u;
     while (c > 32u && (size_t)c * 16 > n) c >>= 1;
@@ -106,6 +101,17 @@ unsigned choose_chunk_free(const Plan* p, size_t n, int geo)
   if (u < 4.0e6) return 128;
   if (u < 16.0e6) return 256;
   return kAutoChunk;
+}
+
+/* chunk length of a call: the measured optimum, rounded up to a multiple of the float phase table's stride so
+ * that every chunk but the first of a call starts on a table row (no rotations) */
+unsigned choose_chunk(const Plan* p, size_t n, int geo)
+{
+  unsigned c = choose_chunk_free(p, n, geo);
+  const unsigned s = p->f0_stride;
+  c = ((c + s - 1) / s) * s;
+  if (c > (unsigned)kMaxChunk) c = kMaxChunk;
+  return c;
 }
 
 template <typename F, int EMIT, int GEO>
@@ -179,24 +185,6 @@ unsigned scan_warps_for(const Plan* p, unsigned chunk, unsigned nchunks, int geo
   if (w > nchunks) w = nchunks;
   if (w < 1) w = 1;
   return w;
-}
-
-/* bins per warp-wide group of a geometry (the halo on either side excluded) */
-unsigned span_of(const Plan* p, int geo, bool no_halo)
-{
-  unsigned wc, halo;
-  if (p->fd == kF32)
-  {
-    wc = geo == GEO_WIDE ? (unsigned)Geo<float, GEO_WIDE>::WC : (unsigned)Geo<float, GEO_NARROW>::WC;
-    halo = (unsigned)Geo<float, GEO_WIDE>::GROUP;
-  }
-  else
-  {
-    wc = geo == GEO_WIDE ? (unsigned)Geo<double, GEO_WIDE>::WC : (unsigned)Geo<double, GEO_NARROW>::WC;
-    halo = (unsigned)Geo<double, GEO_WIDE>::GROUP;
-  }
-  if (p->window == 0 || no_halo) halo = 0;
-  return wc - 2 * halo;
 }
 
 /* one launch of the scan kernel over the bins [bin_base, bin_end) of a call */

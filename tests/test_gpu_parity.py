@@ -723,6 +723,41 @@ def test_streaming_mode_mixed_call_sequences(SDFT, td, fd, window):
         assert cg == co and np.array_equal(_bits(hg), _bits(ho)) and rel_err(ag, ao) <= TOL[fd]
 
 
+@pytest.mark.parametrize("fd", ["f64", "f32"])
+def test_streaming_mode_batch_plan_roi_and_side_stream(SDFT, fd):
+    """Streaming on a BATCH plan (the hand-over counters count per channel), with a region of interest, queued on
+    a torch side stream while the default stream is busy: every channel against its own oracle."""
+    import torch
+    from oracle import Oracle
+    m, ch, hop, calls = 250, 3, 512, 40
+    rng = np.random.default_rng(seed_of("stream-batch", fd))
+    x = rng.uniform(-1, 1, (ch, hop * calls)).astype(np.float32)
+    xt = torch.from_numpy(x).cuda()
+    g = SDFT(m, "hamming", 0.5, td="f32", fd=fd, channels=ch)
+    g.set_streaming(6)
+    g.set_roi(40, 120)
+    side = torch.cuda.Stream()
+    busy = torch.empty(1 << 26, device="cuda")
+    outs = []
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        for c in range(calls):
+            busy.normal_()                                   # unrelated work between the calls, on the same stream
+            seg = xt[:, c * hop:(c + 1) * hop].contiguous()
+            side.synchronize()                               # the promise: samples complete when the call is issued
+            outs.append(g.sdft(seg))
+        y = g.isdft(outs[-1])                                # queued behind the calls in the ordinary way
+    side.synchronize()
+    g._check()
+    got = torch.stack(outs, dim=1).cpu().numpy()             # (ch, calls, hop, 120)
+    for k in range(ch):
+        o = Oracle("f32", fd, m, "hamming", 0.5)
+        want = o.sdft(x[k])
+        w = want.reshape(calls, hop, m)[:, :, 40:160]
+        assert np.abs(got[k] - w).max() <= TOL[fd] * np.abs(want).max(), k
+    assert y.shape == (ch, hop)
+
+
 def test_host_tiling_matches_single_pass(SDFT, monkeypatch):
     """Host destinations are produced in device tiles; tiny tiles must not change a bit."""
     m, n = 64, 5000

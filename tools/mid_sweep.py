@@ -12,6 +12,10 @@ import torch  # noqa: E402
 def main():
     from sdft_b200 import SDFT
     buf = torch.empty(40 << 30, dtype=torch.uint8, device="cuda")
+    print("# Short and mid-size calls: serial vs streaming (B200, tools/mid_sweep.py)\n")
+    print("Device time per call of back-to-back analysis calls on one plan (device buffers, CUDA events, rows into distinct")
+    print("tiles), default geometry / chunk choice, hann, f32 time domain.  Calls above 2^28 bin-updates stay serial on a")
+    print("streaming plan.\n")
     print("| m | FD | n per call | serial us | serial GB/s | streaming(8) us | streaming GB/s | HBM-time us @6454 |")
     print("|---|---|---|---|---|---|---|---|")
     for m, fd in ((512, "f64"), (1024, "f64"), (2048, "f32"), (4096, "f64"), (4096, "f32")):

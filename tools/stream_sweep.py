@@ -24,6 +24,10 @@ def main():
     esz = 16 if a.fd == "f64" else 8
     x = torch.rand(calls * hop, device="cuda") * 2 - 1
     out = torch.empty(calls * hop * m * esz, dtype=torch.uint8, device="cuda")
+    print("# Streaming mode tuning (B200, tools/stream_sweep.py)\n")
+    print("Microseconds per %d-sample call at m = %d (%s frequency domain, hann), %d back-to-back calls issued by" % (hop, m, a.fd, calls))
+    print("sdft_b200_*_sdft_hops into distinct tiles, over streaming depth (1 = serial), warp geometry, chunk length and")
+    print("warps per CTA (auto = the library's choice).\n")
     print("| depth | geo | chunk | warps | us/call | GB/s |")
     print("|---|---|---|---|---|---|")
     depths = (1, 4, 8, 16) if not a.quick else (1, 8)
