@@ -229,6 +229,14 @@ SDFT_B200_API int sdft_b200_channel_shard(size_t channels, size_t world, size_t 
 SDFT_B200_API void* sdft_b200_host_alloc(size_t bytes);
 SDFT_B200_API void sdft_b200_host_free(void* ptr);
 
+/* Device memory for callers without the CUDA toolkit (plain C / C++ like the reference's drivers): a hop buffer
+ * from sdft_b200_device_alloc instead of malloc keeps the rows on the GPU between sdft_sdft_n and sdft_isdft_n
+ * (INTEGRATION.md).  sdft_b200_copy moves bytes between host and device memory in either direction, synchronously,
+ * after the plan's queued work (plan may be NULL: no wait); returns 0 on success. */
+SDFT_B200_API void* sdft_b200_device_alloc(size_t bytes);
+SDFT_B200_API void sdft_b200_device_free(void* ptr);
+SDFT_B200_API int sdft_b200_copy(sdft_b200_plan_t* plan, void* dst, const void* src, size_t bytes);
+
 /* Library build information: "sdft_b200 <version> sm_100a ..." */
 SDFT_B200_API const char* sdft_b200_version(void);
 

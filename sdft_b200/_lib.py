@@ -59,6 +59,9 @@ UNTYPED = {
     "sdft_b200_channel_shard": (_I, [_SZ, _SZ, _SZ] + [ctypes.POINTER(ctypes.c_size_t)] * 2),
     "sdft_b200_host_alloc": (_P, [_SZ]),
     "sdft_b200_host_free": (_V, [_P]),
+    "sdft_b200_device_alloc": (_P, [_SZ]),
+    "sdft_b200_device_free": (_V, [_P]),
+    "sdft_b200_copy": (_I, [_P, _P, _P, _SZ]),
     "sdft_b200_version": (ctypes.c_char_p, []),
     "sdft_b200_debug_trace": (_SZ, [_P, _P, _SZ]),
 }

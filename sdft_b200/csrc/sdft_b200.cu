@@ -456,6 +456,41 @@ extern "C" void sdft_b200_host_free(void* ptr)
   if (ptr) cudaFreeHost(ptr);
 }
 
+/* device memory for callers that are plain C / C++ without the CUDA toolkit (the reference's drivers): a hop
+ * buffer allocated here instead of malloc keeps the rows on the GPU between sdft_sdft_n and sdft_isdft_n */
+extern "C" void* sdft_b200_device_alloc(size_t bytes)
+{
+  void* ptr = nullptr;
+  if (cudaMalloc(&ptr, bytes ? bytes : 1) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return ptr;
+}
+
+extern "C" void sdft_b200_device_free(void* ptr)
+{
+  if (ptr) cudaFree(ptr);
+}
+
+/* synchronous copy between host and device memory in either direction (the runtime works out which is which);
+ * waits for the plan's queued work first when a plan is given.  0 on success. */
+extern "C" int sdft_b200_copy(sdft_b200_plan_t* p, void* dst, const void* src, size_t bytes)
+{
+  if (p)
+  {
+    DeviceGuard on_device(p->device);
+    cudaError_t e = cudaStreamSynchronize(p->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(dst, src, bytes, cudaMemcpyDefault);
+    if (e != cudaSuccess) plan_fail(p, (int)e, "sdft_b200_copy", __FILE__, __LINE__);
+    return p->status;
+  }
+  const cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyDefault);
+  if (e != cudaSuccess) cudaGetLastError();
+  return (int)e;
+}
+
 extern "C" const char* sdft_b200_version(void)
 {
   return "sdft_b200 0.2 (sm_100a; analysis: single-pass chained scan + emit; synthesis: warp reduction; fused round trip)";

@@ -455,8 +455,15 @@ __device__ __forceinline__ F synth_step_impl(Lane& L, const Syn& syn, const F* s
   }
 }
 
+/* register budget of the scan kernel: 2 CTAs of 8 warps per SM (128 registers) by default; -DSDFT_B200_MAXNREG=n
+ * builds a variant with an explicit cap instead (tools/build_variants.py; 4-warp CTAs then fit 64K / (128 n) per SM) */
+#if defined(SDFT_B200_MAXNREG)
+#define SDFT_B200_SCAN_BOUNDS __maxnreg__(SDFT_B200_MAXNREG)
+#else
+#define SDFT_B200_SCAN_BOUNDS __launch_bounds__(kScanWarps * 32, 2)
+#endif
 template <typename F, int WINDOW, bool VEC, int EMIT, int MODE, int GEO>
-__global__ void __launch_bounds__(kScanWarps * 32, 2) scan_emit_kernel(const ChainArgs<F> a)
+__global__ void SDFT_B200_SCAN_BOUNDS scan_emit_kernel(const ChainArgs<F> a)
 {
   typedef EmitGeo<F, WINDOW, GEO> G;
   typedef Arith<F> A;

@@ -84,6 +84,7 @@ int main() { return (use<float, float>() + use<float, double>() + use<double, fl
 
 def test_drivers_compile():
     _compile(os.path.join(DRV, "hop_driver.c"), os.path.join(OUT, "hop_driver_c"), "c")
+    _compile(os.path.join(DRV, "hop_driver_stream.c"), os.path.join(OUT, "hop_driver_stream_c"), "c")
     _compile(os.path.join(DRV, "hop_driver.cpp"), os.path.join(OUT, "hop_driver_cpp"), "cpp")
 
 
@@ -113,3 +114,25 @@ def test_reference_shaped_drivers_match_oracle(lang, golden_dir):
     assert np.allclose(dfts, want_rows)                                         # test/main.py:78
     assert np.abs(dfts - want_rows).max() / np.abs(want_rows).max() <= 1e-9     # BASELINE tolerance
     assert np.allclose(dfts[:24], g["t1000_rows"], rtol=0, atol=1e-12)          # golden rows generated from oracle/_ref
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("depth", [1, 8])
+def test_streaming_c_driver_on_device_buffers(depth, golden_dir):
+    """The reference driver's hop loop (test/test.c:69-83) from plain C with every buffer on the device
+    (sdft_b200_device_alloc, no CUDA toolkit on the caller's side) and the plan in streaming mode: m = 512,
+    64-sample hops over the head of test.wav -- short calls below the 2m period, so every call rolls the history
+    it got from its predecessor."""
+    from oracle import Oracle
+    exe = _compile(os.path.join(DRV, "hop_driver_stream.c"), os.path.join(OUT, "hop_driver_stream_c"), "c")
+    g = np.load(os.path.join(golden_dir, "testwav.npz"))
+    m, hop, nh = 512, 64, 1500
+    x = (g["pcm24"].astype(np.float64) / 8388608.0).astype(np.float32)[50000:50000 + hop * nh]
+    res = subprocess.run([exe, str(m), str(hop), "1", "1", str(depth)], input=x.tobytes(), stdout=subprocess.PIPE, check=True)
+    dfts = np.frombuffer(res.stdout[:nh * m * 16], np.complex128).reshape(nh, m)
+    y = np.frombuffer(res.stdout[nh * m * 16:], np.float32)
+    o = Oracle("f32", "f64", m, 1, 1.0)
+    want = o.sdft(x)
+    want_y = o.isdft(want)
+    assert np.abs(dfts - want[::hop]).max() / np.abs(want).max() <= 1e-9
+    assert np.allclose(y, want_y, rtol=0, atol=2e-6)
