@@ -362,6 +362,27 @@ def other_configs(torch, SDFT, scratch, peak):
                              "us_per_call_streaming_python_loop": t_py * 1e6,
                              "us_per_call_serial_python_loop": t_serial * 1e6, "us_per_call_serial_c_loop": t_serial_c * 1e6,
                              "hbm_time_per_call_us": n * m * 16 / (peak * 1e9) * 1e6}
+    # the reference's per-sample entry points (sdft.h:562, :635) through the drop-in calls with host buffers
+    m1 = 1000
+    g = SDFT(m1, "hann", 1, td="f32", fd="f64")
+    row = np.zeros(m1, np.complex128)
+    rp = row.ctypes.data_as(ctypes.c_void_p)
+    f_s, f_i = g._f("sdft"), g._f("isdft")
+    for _ in range(50):
+        f_s(g._h, ctypes.c_float(0.25), rp)
+        f_i(g._h, rp)
+    t0 = time.perf_counter()
+    for k in range(500):
+        f_s(g._h, ctypes.c_float(0.001 * k), rp)
+    t_one = (time.perf_counter() - t0) / 500
+    t0 = time.perf_counter()
+    for k in range(500):
+        f_i(g._h, rp)
+    t_inv = (time.perf_counter() - t0) / 500
+    g._check()
+    res["single_sample_calls"] = {"workload": "sdft_sdft / sdft_isdft (ONE sample per call, host row), m=1000, f64 FD, hann; wall clock "
+                                              "per call incl. the ctypes call; small calls travel through a pinned mailbox the "
+                                              "kernels read and write in place", "sdft_us": t_one * 1e6, "isdft_us": t_inv * 1e6}
     return res
 
 

@@ -56,11 +56,52 @@ bool release_samples(Plan* p)
   return true;
 }
 
+/* SMALL calls on host buffers (the reference's per-sample sdft_sdft / sdft_isdft, short hops): copy operations,
+ * a second stream and the host copy threads cost more than the data is worth.  The plan keeps a pinned,
+ * device-visible mailbox; the samples are memcpy'd into it, the kernel reads them and writes its rows there in
+ * place (over PCIe, a few KiB), one stream synchronisation, one memcpy out.  About half the latency of the tiled
+ * path for a single sample. */
+constexpr size_t kMailboxSamples = 256;            // per channel
+constexpr size_t kMailboxRowBytes = (size_t)256 << 10;
+
+size_t mailbox_rows_offset(size_t sample_bytes) { return (sample_bytes + 255) / 256 * 256; }
+
+template <typename T, typename F>
+bool small_sdft(Plan* p, size_t n, const T* samples, cx<F>* dfts)
+{
+  const size_t m = row_bins(p), ch = p->channels;
+  const size_t sbytes = ch * n * sizeof(T), rbytes = ch * n * m * sizeof(cx<F>), off = mailbox_rows_offset(sbytes);
+  if (!reserve_mailbox(p, off + rbytes)) return false;
+  memcpy(p->mailbox, samples, sbytes);
+  cx<F>* rows = (cx<F>*)((char*)p->mailbox + off);
+  if (!analysis_device<T, F>(p, n, (const T*)p->mailbox, n, rows, n * m)) return false;
+  CU_TRY(p, cudaStreamSynchronize(p->stream));
+  memcpy(dfts, rows, rbytes);
+  return true;
+}
+
+template <typename T, typename F>
+bool small_isdft(Plan* p, size_t n, const cx<F>* dfts, T* samples)
+{
+  const size_t m = row_bins(p), ch = p->channels;
+  const size_t sbytes = ch * n * sizeof(T), rbytes = ch * n * m * sizeof(cx<F>), off = mailbox_rows_offset(sbytes);
+  if (!reserve_mailbox(p, off + rbytes)) return false;
+  cx<F>* rows = (cx<F>*)((char*)p->mailbox + off);
+  memcpy(rows, dfts, rbytes);
+  if (!synthesis_device<T, F>(p, n, rows, n * m, (T*)p->mailbox, n)) return false;
+  CU_TRY(p, cudaStreamSynchronize(p->stream));
+  memcpy(samples, p->mailbox, sbytes);
+  return true;
+}
+
 template <typename T, typename F>
 bool do_sdft(Plan* p, size_t n, const T* samples, cx<F>* dfts)
 {
   if (n == 0) return true;
   DeviceGuard on_device(p->device);
+  if (n <= kMailboxSamples && p->channels * n * row_bins(p) * sizeof(cx<F>) <= kMailboxRowBytes &&
+      classify(samples) != kDevice && classify(dfts) != kDevice)
+    return small_sdft<T, F>(p, n, samples, dfts);
   bool ok = true;
   const T* x = stage_samples<T>(p, n, samples, &ok);
   if (!ok) return false;
@@ -168,6 +209,9 @@ bool do_isdft(Plan* p, size_t n, const cx<F>* dfts, T* samples)
 {
   if (n == 0) return true;
   DeviceGuard on_device(p->device);
+  if (n <= kMailboxSamples && p->channels * n * row_bins(p) * sizeof(cx<F>) <= kMailboxRowBytes &&
+      classify(samples) != kDevice && classify(dfts) != kDevice)
+    return small_isdft<T, F>(p, n, dfts, samples);
   const size_t m = row_bins(p), ch = p->channels;   // bins per row: the region of interest
   const bool out_dev = classify(samples) == kDevice;
   T* y = samples;

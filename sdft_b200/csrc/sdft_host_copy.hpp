@@ -51,6 +51,14 @@ public:
       for (size_t off = 0; off < s.bytes; off += slice)
         work.push_back({ (char*)s.dst + off, (const char*)s.src + off, (s.bytes - off < slice) ? s.bytes - off : slice });
     if (work.empty()) return;
+    size_t total = 0;
+    for (const CopySeg& w : work) total += w.bytes;
+    if (total < ((size_t)1 << 20))
+    {
+      /* waking the pool costs more than copying a few hundred KiB */
+      for (const CopySeg& w : work) memcpy(w.dst, w.src, w.bytes);
+      return;
+    }
     std::lock_guard<std::mutex> one_caller(run_mutex_);   // plans on different threads take turns
     {
       std::unique_lock<std::mutex> lock(mutex_);

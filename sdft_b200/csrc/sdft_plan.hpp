@@ -72,6 +72,9 @@ struct sdft_b200_plan
   Buffer trace;                  // -DSDFT_B200_TRACE builds: per-CTA phase stamps of the last scan launch
   size_t trace_items = 0;
   void* stage[2] = { nullptr, nullptr };   // pinned host staging for PAGEABLE caller buffers (grow-only)
+  void* mailbox = nullptr;       // pinned, device-visible: samples and rows of SMALL host-buffer calls travel through it
+                                 // without copy operations (the kernels read and write it in place), see do_sdft
+  size_t mailbox_bytes = 0;
   size_t stage_bytes[2] = { 0, 0 };
   cudaEvent_t stage_done[2] = { nullptr, nullptr };
   /* Scratch of the chained scan, one slot per call that may be in flight: inclusive prefixes, block totals,
@@ -216,6 +219,22 @@ PtrKind classify(const void* ptr)
   return kHostPageable;
 }
 
+/* the mailbox of small host-buffer calls: [samples | rows], grow-only */
+bool reserve_mailbox(Plan* p, size_t bytes)
+{
+  if (bytes <= p->mailbox_bytes) return true;
+  if (p->mailbox)
+  {
+    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    CU_TRY(p, cudaFreeHost(p->mailbox));
+    p->mailbox = nullptr;
+    p->mailbox_bytes = 0;
+  }
+  CU_TRY(p, cudaMallocHost(&p->mailbox, bytes));
+  p->mailbox_bytes = bytes;
+  return true;
+}
+
 bool reserve_stage(Plan* p, int b, size_t bytes)
 {
   if (bytes <= p->stage_bytes[b]) return true;
@@ -275,10 +294,18 @@ bool plan_rings(Plan* p, unsigned depth)
   std::vector<void*> hist(depth + 1, nullptr), acc(depth + 1, nullptr);
   for (unsigned i = 0; i <= depth; ++i)
   {
-    CU_TRY(p, cudaMalloc(&hist[i], hbytes));
-    CU_TRY(p, cudaMalloc(&acc[i], abytes));
-    CU_TRY(p, cudaMemset(hist[i], 0, hbytes));
-    CU_TRY(p, cudaMemset(acc[i], 0, abytes));
+    cudaError_t e = cudaMalloc(&hist[i], hbytes);
+    if (e == cudaSuccess) e = cudaMalloc(&acc[i], abytes);
+    if (e == cudaSuccess) e = cudaMemset(hist[i], 0, hbytes);
+    if (e == cudaSuccess) e = cudaMemset(acc[i], 0, abytes);
+    if (e != cudaSuccess)
+    {
+      /* the plan keeps the rings it had; nothing half-built stays behind */
+      for (void* q : hist) if (q) cudaFree(q);
+      for (void* q : acc) if (q) cudaFree(q);
+      plan_fail(p, (int)e, "state rings", __FILE__, __LINE__);
+      return false;
+    }
   }
   if (!p->history.empty())
   {
@@ -427,6 +454,7 @@ void plan_destroy(Plan* p)
   for (int i = 0; i < 2; ++i)
   {
     if (p->stage[i]) cudaFreeHost(p->stage[i]);
+    if (i == 0 && p->mailbox) cudaFreeHost(p->mailbox);
     if (p->stage_done[i]) cudaEventDestroy(p->stage_done[i]);
     if (p->tile_ready[i]) cudaEventDestroy(p->tile_ready[i]);
     if (p->tile_free[i]) cudaEventDestroy(p->tile_free[i]);
