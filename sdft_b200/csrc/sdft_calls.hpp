@@ -62,7 +62,9 @@ bool release_samples(Plan* p)
  * place (over PCIe, a few KiB), one stream synchronisation, one memcpy out.  About half the latency of the tiled
  * path for a single sample. */
 constexpr size_t kMailboxSamples = 256;            // per channel
-constexpr size_t kMailboxRowBytes = (size_t)256 << 10;
+constexpr size_t kMailboxRowBytes = (size_t)256 << 10;    // analysis: rows are WRITTEN to the mailbox (posted PCIe writes)
+constexpr size_t kMailboxReadBytes = (size_t)32 << 10;    // synthesis: rows are READ from it, a round trip per load --
+                                                          // measured slower than the tiled path from 64 KiB on
 
 size_t mailbox_rows_offset(size_t sample_bytes) { return (sample_bytes + 255) / 256 * 256; }
 
@@ -99,7 +101,7 @@ bool do_sdft(Plan* p, size_t n, const T* samples, cx<F>* dfts)
 {
   if (n == 0) return true;
   DeviceGuard on_device(p->device);
-  if (n <= kMailboxSamples && p->channels * n * row_bins(p) * sizeof(cx<F>) <= kMailboxRowBytes &&
+  if (p->mailbox_on && n <= kMailboxSamples && p->channels * n * row_bins(p) * sizeof(cx<F>) <= kMailboxRowBytes &&
       classify(samples) != kDevice && classify(dfts) != kDevice)
     return small_sdft<T, F>(p, n, samples, dfts);
   bool ok = true;
@@ -209,7 +211,7 @@ bool do_isdft(Plan* p, size_t n, const cx<F>* dfts, T* samples)
 {
   if (n == 0) return true;
   DeviceGuard on_device(p->device);
-  if (n <= kMailboxSamples && p->channels * n * row_bins(p) * sizeof(cx<F>) <= kMailboxRowBytes &&
+  if (p->mailbox_on && n <= kMailboxSamples && p->channels * n * row_bins(p) * sizeof(cx<F>) <= kMailboxReadBytes &&
       classify(samples) != kDevice && classify(dfts) != kDevice)
     return small_isdft<T, F>(p, n, dfts, samples);
   const size_t m = row_bins(p), ch = p->channels;   // bins per row: the region of interest

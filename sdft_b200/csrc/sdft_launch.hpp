@@ -346,7 +346,7 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
       launch_chain<F, EMIT_NONE>(p, a, false, warps, sp.geo);
     }
     CU_TRY(p, cudaGetLastError());
-    if (sp.roll_hist) hist_signals += nblocks * ch;
+    if (sp.roll_hist) hist_signals += nblocks * sp.groups * ch;      // every CTA of the launch hands over its slice
     acc_signals += sp.groups * ch;
   }
   if (part || out) prof_mark(p, 0);

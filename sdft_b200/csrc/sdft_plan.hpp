@@ -41,6 +41,7 @@ struct sdft_b200_plan
   int forced_geo = -1;           // SDFT_B200_GEO=wide|narrow: warp geometry (default: per call, choose_geo)
   bool driver_pageable = false;  // SDFT_B200_PAGEABLE=driver: leave pageable buffers to cudaMemcpy (for comparison)
   bool pdl = true;               // SDFT_B200_PDL=0: plain stream-ordered launches
+  bool mailbox_on = true;        // SDFT_B200_MAILBOX=0: small host-buffer calls take the tiled path like everything else (for comparison)
   bool no_split = false;         // SDFT_B200_NO_SPLIT=1: never split a float call into wide body + narrow tail (for comparison)
   size_t tile_bytes = 0;
   unsigned long long launches = 0;
@@ -501,6 +502,7 @@ Plan* plan_create(size_t m, int window, double latency, size_t channels)
     p->driver_pageable = pg && !strcmp(pg, "driver");
     p->pdl = env_size("SDFT_B200_PDL", 1) != 0;
     p->no_split = env_size("SDFT_B200_NO_SPLIT", 0) != 0;
+    p->mailbox_on = env_size("SDFT_B200_MAILBOX", 1) != 0;
     const char* ge = getenv("SDFT_B200_GEO");
     if (ge && !strcmp(ge, "wide")) p->forced_geo = GEO_WIDE;
     if (ge && !strcmp(ge, "narrow")) p->forced_geo = GEO_NARROW;

@@ -42,7 +42,7 @@ namespace sdftb200
  *      failure, not as a hung device.
  *
  *      Between calls.  A call hands three things to the next call on the plan: the 2m-sample history
- *      (written by the CTAs of group 0 in their prologue), the accumulators (written by the last block item
+ *      (written by the call's CTAs in their prologue, a slice each), the accumulators (written by the last block item
  *      of every chain) and, implicitly, the order of completion.  Each hand-over has its own counter
  *      (ChainArgs::sync: [0] history pieces written, [1] accumulator rows written; monotonic, the host knows
  *      the totals), so the consumer can wait for exactly what it needs:
@@ -115,7 +115,7 @@ template <typename F> struct ChainArgs
   unsigned groups;
   unsigned bin_base;       // this launch covers bins [bin_base, bin_end) in `groups` warp-wide groups: everything,
   unsigned bin_end;        // or the wide body / the narrow tail of a split call
-  unsigned roll_hist;      // 1: the CTAs of group 0 write the next history (exactly one launch of a call does)
+  unsigned roll_hist;      // 1: this launch writes the next history, every CTA a slice (exactly one launch of a call does)
   unsigned stage_rows;     // rows of look-back staging in shared memory (scan_stage_rows)
   WindowConst<F> win;
   unsigned long long* trace;   // -DSDFT_B200_TRACE builds only: 8 %globaltimer stamps per CTA, else unused
@@ -282,15 +282,16 @@ __device__ __forceinline__ void chunk_deltas(const ChainArgs<F>& a, unsigned ch,
     sdelta[i] = (F)diff * a.scale;
   }
 }
-/* the history the next call starts from; entries are dealt out over the block items of group 0 */
+/* the history the next call starts from; entries are dealt out over ALL CTAs of the channel (a one-sample call at
+ * m = 4096 still moves 8192 entries: one warp alone needs 40 us for that, the call's 69 CTAs together 2 us) */
 template <typename T, typename F>
-__device__ __forceinline__ void roll_history(const ChainArgs<F>& a, unsigned ch, unsigned jb)
+__device__ __forceinline__ void roll_history(const ChainArgs<F>& a, unsigned ch, unsigned slice, unsigned nslices)
 {
   const unsigned period = a.sched.period;
   const T* x = (const T*)a.samples + (size_t)ch * a.sample_stride;
   const T* ho = (const T*)a.hist_old + (size_t)ch * period;
   T* hn = (T*)a.hist_new + (size_t)ch * period;
-  for (unsigned i = jb * blockDim.x + threadIdx.x; i < period; i += a.nblocks * blockDim.x)
+  for (unsigned i = slice * blockDim.x + threadIdx.x; i < period; i += nslices * blockDim.x)
   {
     const unsigned long long pos = a.sched.n + i;   // position inside history || samples
     hn[i] = (pos < period) ? __ldcg(ho + pos) : x[pos - period];
@@ -499,12 +500,10 @@ __global__ void SDFT_B200_SCAN_BOUNDS scan_emit_kernel(const ChainArgs<F> a)
     {
       /* streaming: the previous call may still be writing the history this CTA reads -- for the deltas of
        * the call's first 2m samples (its first chunk is the earliest) or for rolling a short call's history */
-      const unsigned per = a.channels * a.groups;
-      const unsigned jb0 = t / per;
-      const unsigned g0 = (t - jb0 * per) % a.groups;
+      const unsigned jb0 = t / (a.channels * a.groups);
       const unsigned first = jb0 * (blockDim.x >> 5);
       const bool reads_hist = (first < a.sched.nchunks && chunk_span(a.sched, first).t0 < a.sched.period) ||
-                              (g0 == 0 && a.roll_hist && a.sched.n < a.sched.period);
+                              (a.roll_hist && a.sched.n < a.sched.period);
       if (reads_hist) wait_counter(a.prev_sync, a.prev_hist_target, a.error);
     }
   }
@@ -533,10 +532,10 @@ __global__ void SDFT_B200_SCAN_BOUNDS scan_emit_kernel(const ChainArgs<F> a)
     else chunk_deltas<float, F>(a, ch, cs, sdelta, lane);
     if (lane < 2) sdelta[cs.len + lane] = (F)0;
   }
-  if (group == 0 && a.roll_hist)
+  if (a.roll_hist)
   {
-    if (a.td_double) roll_history<double, F>(a, ch, jb);
-    else roll_history<float, F>(a, ch, jb);
+    if (a.td_double) roll_history<double, F>(a, ch, jb * a.groups + group, a.nblocks * a.groups);
+    else roll_history<float, F>(a, ch, jb * a.groups + group, a.nblocks * a.groups);
     if (a.handover)
     {
       /* hand-over: this CTA's piece of the next call's history is written */
