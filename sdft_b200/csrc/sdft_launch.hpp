@@ -90,7 +90,7 @@ unsigned choose_chunk_free(const Plan* p, size_t n, int geo)
     /* profiles/r01_geo_sweep.md: narrow warps like longer chunks earlier, but never so long that a chain
      * has fewer than 16 chunks.  Streaming calls overlap their neighbours, so the latency of a chunk's serial
      * steps hides behind other calls' work and the per-chunk overheads decide: 128 from the start
-     * (profiles/r02_v1_stream_sweep.md: 6.7 us instead of 7.3-7.8 per 4096-sample call at m = 512) */
+     * (profiles/r02_stream_sweep.md: 6.7 us instead of 7.3-7.8 per 4096-sample call at m = 512) */
     unsigned c = (u < 16384.0) ? 32u : ((u < 30.0e3) ? 64u : 128u);
     if (p->stream_depth > 1 && c < 128u) c = 128u;
     while (c > 32u && (size_t)c * 16 > n) c >>= 1;
@@ -216,7 +216,7 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   const double work = (double)n * (double)m * (double)ch;
   /* overlap pays where a call's fixed latencies (ticket, first look-back, drain: ~10 us) are a visible share of
    * it: up to ~2^28 bin-updates (0.7 ms).  Longer calls gain nothing and one shape was measured slower
-   * (profiles/r02_v1_mid_sweep.md: m = 4096 float, 2^18 samples per call), so they stay serial. */
+   * (profiles/r02_mid_sweep.md: m = 4096 float, 2^18 samples per call), so they stay serial. */
   const bool may_flow = depth > 1 && allow_flow && !part && work <= 268435456.0;
 
   ScanPart parts[2];

@@ -2,7 +2,7 @@
 bench lines, launch list + shares, the ncu --set full summary of the dominant kernels (one unit per row, see
 ncu_summary.py), emit_traffic.json (DRAM bytes per bin-update of the row kernel) and fused_fp64.json (FP64
 instructions per bin-update of the fused kernel), which bench.py scales by the launch it times.
-Usage: python tools/publish_profiles.py <tag> <label>      e.g.  r2f r02_v1"""
+Usage: python tools/publish_profiles.py <tag> <label>      e.g.  r2n r02"""
 import json
 import os
 import shutil
