@@ -362,6 +362,26 @@ def other_configs(torch, SDFT, scratch, peak):
                              "us_per_call_streaming_python_loop": t_py * 1e6,
                              "us_per_call_serial_python_loop": t_serial * 1e6, "us_per_call_serial_c_loop": t_serial_c * 1e6,
                              "hbm_time_per_call_us": n * m * 16 / (peak * 1e9) * 1e6}
+    # row-pointer variant against the contiguous call (sdft.h:622-628 vs :607-613), device rows, n = 2^16, m = 1024
+    m, n = 1024, 1 << 16
+    g = SDFT(m, "hann", 1, td="f32", fd="f64")
+    g._use_torch_stream()
+    x = torch.rand(n, device=raw.device) * 2 - 1
+    rows_bytes = n * m * 16
+    base = raw.data_ptr()
+    contiguous = (ctypes.c_void_p * n)(*[base + i * m * 16 for i in range(n)])
+    perm = np.random.default_rng(3).permutation(n)
+    scattered = (ctypes.c_void_p * n)(*[base + int(perm[i]) * m * 16 for i in range(n)])
+    t_n = timed(lambda: g._f("sdft_n")(g._h, n, ptr(x), ptr(raw)))
+    t_nd = timed(lambda: g._f("sdft_nd")(g._h, n, ptr(x), contiguous))
+    t_nds = timed(lambda: g._f("sdft_nd")(g._h, n, ptr(x), scattered))
+    g._check()
+    res["row_pointer_variant"] = {"workload": "sdft_sdft_nd vs sdft_sdft_n, n=65536, m=1024, f64 FD, device samples and rows: row "
+                                              "pointers into one matrix (one run: the contiguous path) and in shuffled order "
+                                              "(tile + one scatter kernel per tile)",
+                                  "sdft_n_GBps": rows_bytes / t_n / 1e9, "sdft_nd_contiguous_GBps": rows_bytes / t_nd / 1e9,
+                                  "sdft_nd_scattered_GBps": rows_bytes / t_nds / 1e9,
+                                  "nd_contiguous_time_over_n": t_nd / t_n, "nd_scattered_time_over_n": t_nds / t_n}
     # the reference's per-sample entry points (sdft.h:562, :635) through the drop-in calls with host buffers
     m1 = 1000
     g = SDFT(m1, "hann", 1, td="f32", fd="f64")
@@ -621,9 +641,10 @@ def run_b200_arm(args, rank, local_rank, world):
     d2h_gbps = args.steps * n_e * m * 16 / t_e2e / 1e9
     e2e = {"value": world * args.steps * n_e * m / t_e2e, "unit": UNIT, "h2d_bytes_per_step": n_e * 4,
            "d2h_bytes_per_step": n_e * m * 16, "ms_per_step": t_e2e / args.steps * 1e3,
-           "bound": "pcie: the drop-in call delivers 16 B per bin-update to HOST memory; hop_pattern / roundtrip below "
-                    "are what a caller gets who keeps the rows on the device",
-           "d2h_GBps_per_gpu": d2h_gbps, "pcie_ceiling_GBps_per_gpu": pcie_gbps,
+           "bound": "pcie",
+           "bound_note": "the drop-in call delivers 16 B per bin-update to HOST memory; hop_pattern / roundtrip below "
+                         "are what a caller gets who keeps the rows on the device",
+           "d2h_GBps_per_gpu": d2h_gbps, "pcie_ceiling_GBps": pcie_gbps, "pcie_ceiling_GBps_per_gpu": pcie_gbps,
            "pcie_ceiling_GBps_all_gpus": pcie_gbps * world, "frac_of_pcie": d2h_gbps / pcie_gbps,
            "pcie_ceiling_how": "plain pinned cudaMemcpyAsync device->host of the same %.1f GiB buffer, %d rank(s) "
                                "concurrently, wall clock, max over ranks" % (n_e * m * 16 / 2 ** 30, world),
