@@ -433,10 +433,10 @@ bool do_sdft_nd(Plan* p, size_t n, const T* samples, cx<F>** rows_out)
         if (!dev_rows[i]) segs.push_back({ rows_out[t0 + i], (const char*)p->stage[0] + i * row_bytes, row_bytes });
       HostCopier::get().run(segs);
     }
-    CU_TRY(p, cudaStreamSynchronize(p->stream));      // dev_rows / the tile are reused by the next tile
+    /* the tile and the pointer list are reused in stream order: no host wait for device rows (the pageable pointer
+     * list has been staged by the time cudaMemcpyAsync returns) */
   }
-  p->samples_in_flight = false;
-  return true;
+  return release_samples(p);
 }
 
 template <typename T, typename F>
@@ -503,7 +503,7 @@ bool do_isdft_nd(Plan* p, size_t n, const cx<F>** rows_in, T* samples)
       CU_TRY(p, cudaGetLastError());
     }
     if (!synthesis_device<T, F>(p, len, (const cx<F>*)p->tile[0].ptr, len * m, y + t0, n)) return false;
-    CU_TRY(p, cudaStreamSynchronize(p->stream));
+    if (ndev < len) CU_TRY(p, cudaStreamSynchronize(p->stream));     // the staging buffer is refilled by the next tile
   }
   if (!out_dev)
   {
