@@ -288,6 +288,20 @@ class SDFT:
         self._lib.sdft_b200_set_streaming(self._h, int(depth))
         self._check()
 
+    def streaming(self, depth=8):
+        """``with plan.streaming(8): ...`` -- streaming mode for the block, plain stream order again afterwards
+        (leaving the block waits for the calls queued inside it)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            self.set_streaming(depth)
+            try:
+                yield self
+            finally:
+                self.set_streaming(1)
+        return scope()
+
     def sdft_hops(self, samples, hop, out):
         """The reference drivers' hop loop issued from inside the library: `out[h] = sdft(samples[h*hop:(h+1)*hop])`
         for CUDA tensors `samples` (nhops*hop,) and `out` (nhops, hop, bins)."""

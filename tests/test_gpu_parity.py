@@ -649,6 +649,11 @@ def test_streaming_mode_endless_hops(SDFT, fd, depth):
         return g, torch.view_as_real(out)
 
     serial, want = run(1, 64, False)
+    scoped = SDFT(m, "hann", 1, td="f32", fd=fd)
+    scoped.set_chunk(64)
+    with scoped.streaming(depth):                 # the context-manager spelling; leaves the plan serial again
+        first = torch.view_as_real(scoped.sdft(xt[:hop]))
+    assert torch.equal(first, want[0])
     flow, got = run(depth, 64, False)
     assert torch.equal(got, want)
     for a, b in zip(flow.state(), serial.state()):
