@@ -199,7 +199,6 @@ __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v)
 {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
-constexpr unsigned long long kSpinLimitNsFwd = 20ull * 1000ull * 1000ull * 1000ull;
 /* one thread: wait until the monotonic counter has reached `target` (wrap-safe), acquire what its writers released */
 __device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target, unsigned* error)
 {
@@ -210,7 +209,7 @@ __device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned targe
     if (++spins < 64u) continue;
     __nanosleep(100);
     if (t_start == 0) t_start = global_timer_ns();
-    else if (global_timer_ns() - t_start > kSpinLimitNsFwd)
+    else if (global_timer_ns() - t_start > kSpinLimitNs)
     {
       atomicExch(error, 1u);
       break;
