@@ -177,6 +177,9 @@ SDFT_B200_API int sdft_b200_device(const sdft_b200_plan_t* plan);
 SDFT_B200_API size_t sdft_b200_table_bytes(const sdft_b200_plan_t* plan);
 /* number of kernels this plan has launched so far (bench.py reports it as gpu_launches) */
 SDFT_B200_API unsigned long long sdft_b200_launch_count(const sdft_b200_plan_t* plan);
+/* number of analysis calls that ran as a wide body plus a narrow tail of bins in one launch (long float calls whose
+ * last warp group would be mostly empty) -- introspection for the tests */
+SDFT_B200_API unsigned long long sdft_b200_split_count(const sdft_b200_plan_t* plan);
 
 /* CUDA-event timing of the dominant kernels on the plan's stream, for roofline reporting.
  * sdft_b200_kernel_ms returns the summed duration (ms) of the launches of kernel class `which`

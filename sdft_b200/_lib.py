@@ -48,6 +48,7 @@ UNTYPED = {
     "sdft_b200_device": (_I, [_P]),
     "sdft_b200_table_bytes": (_SZ, [_P]),
     "sdft_b200_launch_count": (ctypes.c_ulonglong, [_P]),
+    "sdft_b200_split_count": (ctypes.c_ulonglong, [_P]),
     "sdft_b200_set_profiling": (_I, [_P, _I]),
     "sdft_b200_kernel_ms": (_D, [_P, _I, ctypes.POINTER(ctypes.c_ulonglong)]),
     "sdft_b200_get_twiddles": (_I, [_P, _P, _P]),

@@ -229,6 +229,7 @@ extern "C" size_t sdft_b200_channels(const sdft_b200_plan_t* p) { return p ? p->
 extern "C" size_t sdft_b200_table_bytes(const sdft_b200_plan_t* p) { return p ? p->table_bytes : 0; }
 extern "C" int sdft_b200_device(const sdft_b200_plan_t* p) { return p ? p->device : -1; }
 extern "C" unsigned long long sdft_b200_launch_count(const sdft_b200_plan_t* p) { return p ? p->launches : 0; }
+extern "C" unsigned long long sdft_b200_split_count(const sdft_b200_plan_t* p) { return p ? p->split_calls : 0; }
 
 extern "C" int sdft_b200_get_twiddles(sdft_b200_plan_t* p, void* analysis, void* synthesis)
 {

@@ -173,6 +173,38 @@ void launch_chain(Plan* p, const ChainArgs<F>& a, bool vec, unsigned warps, int 
   else launch_chain_geo<F, EMIT, GEO_WIDE>(p, a, vec, warps);
 }
 
+/* one launch for the two chain sets of a split call (scan_emit_mixed_kernel): wide body + narrow tail, default
+ * arithmetic mode, a window with taps (the boxcar window has no halo and never leaves a short last group) */
+template <typename F, int EMIT>
+void launch_mixed(Plan* p, const ChainArgs<F>& body, const ChainArgs<F>& tail, unsigned every, bool vec, unsigned warps)
+{
+  const size_t smem_b = scan_smem_bytes<F, GEO_WIDE>(warps, body.sched.chunk) + (size_t)body.stage_rows * Geo<F, GEO_WIDE>::WC * sizeof(cx<F>);
+  const size_t smem_t = scan_smem_bytes<F, GEO_NARROW>(warps, tail.sched.chunk) + (size_t)tail.stage_rows * Geo<F, GEO_NARROW>::WC * sizeof(cx<F>);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = p->pdl ? 1 : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(body.total_blocks + tail.total_blocks);
+  cfg.blockDim = dim3(warps * 32);
+  cfg.dynamicSmemBytes = smem_b > smem_t ? smem_b : smem_t;
+  cfg.stream = p->stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define SDFT_MIXED_CASE(W)                                                                                       \
+  case W:                                                                                                        \
+    if (vec) cudaLaunchKernelEx(&cfg, scan_emit_mixed_kernel<F, W, true, EMIT, MODE_FAST>, body, tail, every);   \
+    else cudaLaunchKernelEx(&cfg, scan_emit_mixed_kernel<F, W, false, EMIT, MODE_FAST>, body, tail, every);      \
+    break;
+  switch (p->window)
+  {
+    SDFT_MIXED_CASE(1)
+    SDFT_MIXED_CASE(2)
+    SDFT_MIXED_CASE(3)
+  }
+#undef SDFT_MIXED_CASE
+  p->launches++;
+}
+
 /* warps (= consecutive chunks) per scan/emit CTA */
 unsigned scan_warps_for(const Plan* p, unsigned chunk, unsigned nchunks, int geo)
 {
@@ -187,24 +219,25 @@ unsigned scan_warps_for(const Plan* p, unsigned chunk, unsigned nchunks, int geo
   return w;
 }
 
-/* one launch of the scan kernel over the bins [bin_base, bin_end) of a call */
+/* one chain set of a call: the bins [bin_base, bin_end) in `groups` warp-wide groups of one geometry */
 struct ScanPart
 {
   int geo;
   unsigned bin_base, bin_end, groups;
   unsigned slot_id;
   bool roll_hist;      // writes the next history (the first part of a call)
-  bool last;           // counts the call as completed (the last part of a call)
+  unsigned warps;
 };
 
 /* production path: the single-pass chained scan/emit kernel (deltas and history are its prologue).
  *
- * A call is ONE launch, except: float rows whose last wide warp group would be mostly empty (m = 2048: the 9th
- * group holds 64 of its 248 bins and still issues a full warp's instructions -- the float kernel is bound by
- * FP32 issue, so that is 8 % of the time).  Such a call is split by BINS into a wide body over the full groups
- * and a narrow tail launch over the remaining bins (half the instructions per step).  Bins are independent
- * (every group has its own carry chain), so the two launches share nothing but the samples, the state buffers
- * (each writes the accumulators of the bins it owns) and the hand-over counters. */
+ * A call is one chain set, except: long float calls whose last wide warp group would be mostly empty (m = 2048:
+ * the 9th group holds 64 of its 248 bins and still issues a full warp's instructions -- the float kernel is bound
+ * by instruction issue, so that is 8 % of the time).  Such a call is split by BINS into a wide body over the full
+ * groups and a narrow tail over the remaining bins (half the instructions per step), both in ONE launch
+ * (scan_emit_mixed_kernel) so that the tail's few warps share the machine with the body.  Bins are independent
+ * (every group has its own carry chain): the two sets share nothing but the samples, the state buffers (each
+ * writes the accumulators of the bins it owns) and the hand-over counters. */
 template <typename T, typename F>
 bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out, size_t out_stride, F* part = nullptr,
                       const F* syn_ab = nullptr, bool syn_unit = false, bool allow_flow = false)
@@ -221,7 +254,7 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
 
   ScanPart parts[2];
   int nparts = 1;
-  parts[0] = { geo, 0u, m, groups_for(p, geo, part != nullptr), 0u, true, true };
+  parts[0] = { geo, 0u, m, groups_for(p, geo, part != nullptr), 0u, true, 0u };
   if (geo == GEO_WIDE && p->fd == kF32 && p->mode == MODE_FAST && !part && !may_flow && p->window != 0 && p->forced_geo < 0 &&
       work >= 67108864.0 && !p->no_split)
   {
@@ -229,8 +262,8 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
     const unsigned full = m / span_w, rest = m - full * span_w;
     if (full >= 1 && full <= 11 && rest > 0 && rest <= span_n)
     {
-      parts[0] = { GEO_WIDE, 0u, full * span_w, full, 0u, true, false };
-      parts[1] = { GEO_NARROW, full * span_w, m, 1u, 0u, false, true };
+      parts[0] = { GEO_WIDE, 0u, full * span_w, full, 0u, true, 0u };
+      parts[1] = { GEO_NARROW, full * span_w, m, 1u, 0u, false, 0u };
       nparts = 2;
     }
   }
@@ -239,14 +272,17 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   const size_t ring = p->history.size();
   const unsigned prev_slot = p->prev_slot;
   unsigned flow = 0, first_slot = 0, hist_signals = 0, acc_signals = 0;
-  if (part || out) prof_mark(p, 0);
+  ChainArgs<F> args[2];
   for (int q = 0; q < nparts; ++q)
   {
     ScanPart& sp = parts[q];
     const unsigned chunk = choose_chunk(p, n, sp.geo);
     const Schedule sched = make_schedule(p->cursor, n, m, chunk);
     const size_t wc = (sp.geo == GEO_NARROW) ? (size_t)Geo<F, GEO_NARROW>::WC : (size_t)Geo<F, GEO_WIDE>::WC;
-    const unsigned warps = scan_warps_for(p, chunk, sched.nchunks, sp.geo);
+    /* both chain sets of a split call run in one launch: one CTA width */
+    unsigned warps = (q == 0) ? scan_warps_for(p, chunk, sched.nchunks, sp.geo) : parts[0].warps;
+    if (warps > (unsigned)kSmemSamples / chunk) warps = (unsigned)kSmemSamples / chunk;
+    sp.warps = warps;
     const unsigned nblocks = (sched.nchunks + warps - 1) / warps;
     const size_t items = (size_t)ch * nblocks * sp.groups;
     if (items >= (1ull << 31))
@@ -279,7 +315,7 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
     }
     slot.epoch++;
 
-    ChainArgs<F> a;
+    ChainArgs<F>& a = args[q];
     a.sched = sched;
     a.samples = x;
     a.sample_stride = x_stride;
@@ -296,18 +332,19 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
     a.flags = (unsigned*)slot.flags.ptr;
     a.error = p->control;
     a.handover = depth > 1 ? 1u : 0u;
-    a.completed = (depth > 1 && sp.last) ? p->control + 1 : nullptr;
+    a.completed = depth > 1 ? p->control + 1 : nullptr;
     a.completed_target = (unsigned)(seq - depth + 1);      // modulo 2^32, compared wrap-safe; no wait for the first calls:
     a.wait_completed = (seq >= depth) ? 1u : 0u;
     a.ticket = p->control + 2 + 4 * sp.slot_id;
     a.sync = p->control + 3 + 4 * first_slot;          // both launches of a split call hand over through one pair of counters
-    a.finished = p->control + 5 + 4 * sp.slot_id;
+    a.finished = p->control + 5 + 4 * first_slot;      // ... and count their CTAs out together
     a.prev_sync = p->control + 3 + 4 * prev_slot;
     a.prev_hist_target = p->slots[prev_slot].hist_total;
     a.prev_acc_target = p->slots[prev_slot].acc_total;
     a.flow = flow;
     a.epoch = slot.epoch;
     a.total_blocks = (unsigned)items;
+    a.finish_blocks = (unsigned)items;
     a.nblocks = nblocks;
     a.channels = ch;
     a.m = m;
@@ -326,29 +363,45 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
     a.win = make_window_const<F>(p->m, p->window);   // sdft.h:422, :371
     a.trace = nullptr;
 #if defined(SDFT_B200_TRACE)
-    if (reserve(p, p->trace, items * 8 * sizeof(unsigned long long)))
+    if (q == 0 && reserve(p, p->trace, items * 8 * sizeof(unsigned long long)))
     {
       a.trace = (unsigned long long*)p->trace.ptr;
       p->trace_items = items;
     }
 #endif
-    if (part)
-    {
-      if (syn_unit) launch_chain<F, EMIT_SYNTH_UNIT>(p, a, false, warps, sp.geo);   // all imaginary-part weights are zero
-      else launch_chain<F, EMIT_SYNTH>(p, a, false, warps, sp.geo);
-    }
-    else if (out)
-    {
-      launch_chain<F, EMIT_ROWS>(p, a, can_vectorize<F>(p, out, out_stride), warps, sp.geo);
-    }
-    else
-    {
-      launch_chain<F, EMIT_NONE>(p, a, false, warps, sp.geo);
-    }
-    CU_TRY(p, cudaGetLastError());
     if (sp.roll_hist) hist_signals += nblocks * sp.groups * ch;      // every CTA of the launch hands over its slice
     acc_signals += sp.groups * ch;
   }
+  if (part || out) prof_mark(p, 0);
+  if (nparts == 2)
+  {
+    /* the tail set must have the same CTA width as the body (it may have been clipped by its chunk length) */
+    if (parts[1].warps != parts[0].warps)
+    {
+      plan_fail(p, SDFT_B200_ERR_ARG, "analysis: split call with two CTA widths", __FILE__, __LINE__);
+      return false;
+    }
+    const unsigned total = args[0].total_blocks + args[1].total_blocks;
+    args[0].finish_blocks = args[1].finish_blocks = total;
+    const unsigned every = total / args[1].total_blocks;          // every `every`-th ticket is a tail ticket
+    p->split_calls++;
+    if (out) launch_mixed<F, EMIT_ROWS>(p, args[0], args[1], every, can_vectorize<F>(p, out, out_stride), parts[0].warps);
+    else launch_mixed<F, EMIT_NONE>(p, args[0], args[1], every, false, parts[0].warps);
+  }
+  else if (part)
+  {
+    if (syn_unit) launch_chain<F, EMIT_SYNTH_UNIT>(p, args[0], false, parts[0].warps, parts[0].geo);   // all imaginary-part weights are zero
+    else launch_chain<F, EMIT_SYNTH>(p, args[0], false, parts[0].warps, parts[0].geo);
+  }
+  else if (out)
+  {
+    launch_chain<F, EMIT_ROWS>(p, args[0], can_vectorize<F>(p, out, out_stride), parts[0].warps, parts[0].geo);
+  }
+  else
+  {
+    launch_chain<F, EMIT_NONE>(p, args[0], false, parts[0].warps, parts[0].geo);
+  }
+  CU_TRY(p, cudaGetLastError());
   if (part || out) prof_mark(p, 0);
   /* what this call will have handed over once its group-0 CTAs / last block items are through */
   p->slots[first_slot].hist_total += hist_signals;

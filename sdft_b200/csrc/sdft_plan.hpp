@@ -45,6 +45,7 @@ struct sdft_b200_plan
   bool no_split = false;         // SDFT_B200_NO_SPLIT=1: never split a float call into wide body + narrow tail (for comparison)
   size_t tile_bytes = 0;
   unsigned long long launches = 0;
+  unsigned long long split_calls = 0;    // calls that ran as wide body + narrow tail in one launch (sdft_launch.hpp)
 
   MirrorMap mirrors;
   int mode = 0;                  // MODE_MODULATED / MODE_FAST (double frequency domain only)

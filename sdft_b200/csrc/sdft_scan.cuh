@@ -101,7 +101,8 @@ template <typename F> struct ChainArgs
   unsigned completed_target;   // streaming: calls that must have completed before this one may touch its slot (mod 2^32)
   unsigned wait_completed;     // 0 for the first `depth` calls on fresh rings: nothing to wait for
   unsigned epoch;
-  unsigned total_blocks;   // nblocks * channels * groups
+  unsigned total_blocks;   // nblocks * channels * groups: the tickets of this chain set
+  unsigned finish_blocks;  // CTAs of the whole launch (this chain set, plus the other one of a mixed launch)
   unsigned nblocks;        // block items per chain: ceil(nchunks / warps per CTA)
   unsigned channels;
   unsigned m;
@@ -455,15 +456,12 @@ __device__ __forceinline__ F synth_step_impl(Lane& L, const Syn& syn, const F* s
   }
 }
 
-/* register budget of the scan kernel: 2 CTAs of 8 warps per SM (128 registers) by default; -DSDFT_B200_MAXNREG=n
- * builds a variant with an explicit cap instead (tools/build_variants.py; 4-warp CTAs then fit 64K / (128 n) per SM) */
-#if defined(SDFT_B200_MAXNREG)
-#define SDFT_B200_SCAN_BOUNDS __maxnreg__(SDFT_B200_MAXNREG)
-#else
-#define SDFT_B200_SCAN_BOUNDS __launch_bounds__(kScanWarps * 32, 2)
-#endif
+/* everything a CTA does once it holds its work ticket (phases 0, A, B, C of the header comment), for one
+ * instantiation of the lane engine.  `a.total_blocks` is what the TICKETS of this chain set run to; the kernels
+ * below take the ticket and decide which chain set it belongs to. */
 template <typename F, int WINDOW, bool VEC, int EMIT, int MODE, int GEO>
-__global__ void SDFT_B200_SCAN_BOUNDS scan_emit_kernel(const ChainArgs<F> a)
+__device__ __forceinline__ void scan_emit_body(const ChainArgs<F>& a, const unsigned ticket, unsigned char* smem_raw,
+                                               unsigned* s_warps_done_ptr)
 {
   typedef EmitGeo<F, WINDOW, GEO> G;
   typedef Arith<F> A;
@@ -473,41 +471,13 @@ __global__ void SDFT_B200_SCAN_BOUNDS scan_emit_kernel(const ChainArgs<F> a)
   typedef StageOps<F, FUSED> S;
   /* dynamic shared memory, sized by the launch (scan_smem_bytes): deltas of the CTA's chunks, their
    * totals, the carry at the CTA's first chunk */
-  extern __shared__ __align__(32) unsigned char smem_raw[];
-  __shared__ unsigned s_ticket;
-  __shared__ unsigned s_warps_done;
   const unsigned nwarps = blockDim.x >> 5;
   F* sdelta_all = reinterpret_cast<F*>(smem_raw);
   cx<F>* stot_all = reinterpret_cast<cx<F>*>(smem_raw + (size_t)nwarps * (a.sched.chunk + kDeltaPad) * sizeof(F));
   cx<F>* scarry = stot_all + (size_t)nwarps * G::WC;
   cx<F>* sstage = scarry + G::WC;                            // look-back staging, a.stage_rows rows
 #define stot(u) (stot_all + (size_t)(u) * G::WC)
-
-  /* programmatic dependent launch (see launch_chain): nothing of the previous kernel in the stream may be
-   * read or overwritten before it has completed; dependents of THIS kernel may start filling SMs as
-   * soon as every CTA of it has got this far */
-  if (!a.flow) grid_dependency_wait();
-  asm volatile("griddepcontrol.launch_dependents;");
-  if (threadIdx.x == 0)
-  {
-    s_warps_done = 0;
-    if (a.flow && a.wait_completed) wait_counter(a.completed, a.completed_target, a.error);   // the slot's previous user is through
-    const unsigned t = atomicAdd(a.ticket, 1u);
-    if (t == a.total_blocks - 1) *a.ticket = 0;   // last ticket of the launch: rearm the slot for its next call
-    s_ticket = t;
-    if (a.flow)
-    {
-      /* streaming: the previous call may still be writing the history this CTA reads -- for the deltas of
-       * the call's first 2m samples (its first chunk is the earliest) or for rolling a short call's history */
-      const unsigned jb0 = t / (a.channels * a.groups);
-      const unsigned first = jb0 * (blockDim.x >> 5);
-      const bool reads_hist = (first < a.sched.nchunks && chunk_span(a.sched, first).t0 < a.sched.period) ||
-                              (a.roll_hist && a.sched.n < a.sched.period);
-      if (reads_hist) wait_counter(a.prev_sync, a.prev_hist_target, a.error);
-    }
-  }
-  __syncthreads();
-  const unsigned ticket = s_ticket;
+#define s_warps_done (*s_warps_done_ptr)
   SDFT_B200_STAMP(0);   // ticket taken
   /* (block item, channel, group): the chains of all channels and groups advance together */
   const unsigned per_block = a.channels * a.groups;
@@ -764,7 +734,7 @@ __global__ void SDFT_B200_SCAN_BOUNDS scan_emit_kernel(const ChainArgs<F> a)
     }
   }
   SDFT_B200_STAMP(5);   // carries distributed, replay starts
-  if (!valid) { warp_finish(&s_warps_done, nwarps, a.finished, a.total_blocks, a.completed, a.handover); return; }
+  if (!valid) { warp_finish(&s_warps_done, nwarps, a.finished, a.finish_blocks, a.completed, a.handover); return; }
 
   /* ---- phase C: replay from the carry and stream the rows out ---- */
   if (EMIT == EMIT_ROWS)
@@ -772,7 +742,7 @@ __global__ void SDFT_B200_SCAN_BOUNDS scan_emit_kernel(const ChainArgs<F> a)
     /* groups without a bin inside the region of interest have done their share (the carries): no rows */
     if (a.bin_base + group * (unsigned)G::SPAN >= roi_end || a.bin_base + (group + 1u) * (unsigned)G::SPAN <= roi_first)
     {
-      warp_finish(&s_warps_done, nwarps, a.finished, a.total_blocks, a.completed, a.handover);
+      warp_finish(&s_warps_done, nwarps, a.finished, a.finish_blocks, a.completed, a.handover);
       return;
     }
     const size_t row_stride = a.roi_count;
@@ -882,9 +852,82 @@ SDFT_B200_PRAGMA_UNROLL(SDFT_B200_EMIT_UNROLL)
     }
   }
   SDFT_B200_STAMP(6);   // warp 0 finished its rows
-  warp_finish(&s_warps_done, nwarps, a.finished, a.total_blocks, a.completed, a.handover);   // completes only after the call before it
+  warp_finish(&s_warps_done, nwarps, a.finished, a.finish_blocks, a.completed, a.handover);   // completes only after the call before it
 }
 #undef stot
+#undef s_warps_done
+
+/* register budget of the scan kernels: 2 CTAs of 8 warps per SM (128 registers) by default; -DSDFT_B200_MAXNREG=n
+ * builds a variant with an explicit cap instead (tools/build_variants.py; measured: the default is the best) */
+#if defined(SDFT_B200_MAXNREG)
+#define SDFT_B200_SCAN_BOUNDS __maxnreg__(SDFT_B200_MAXNREG)
+#else
+#define SDFT_B200_SCAN_BOUNDS __launch_bounds__(kScanWarps * 32, 2)
+#endif
+
+/* one call = one chain set = one launch */
+template <typename F, int WINDOW, bool VEC, int EMIT, int MODE, int GEO>
+__global__ void SDFT_B200_SCAN_BOUNDS scan_emit_kernel(const ChainArgs<F> a)
+{
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  __shared__ unsigned s_ticket;
+  __shared__ unsigned s_done;
+  /* programmatic dependent launch (see launch_chain): nothing of the previous kernel in the stream may be
+   * read or overwritten before it has completed; dependents of THIS kernel may start filling SMs as
+   * soon as every CTA of it has got this far */
+  if (!a.flow) grid_dependency_wait();
+  asm volatile("griddepcontrol.launch_dependents;");
+  if (threadIdx.x == 0)
+  {
+    s_done = 0;
+    if (a.flow && a.wait_completed) wait_counter(a.completed, a.completed_target, a.error);   // the slot's previous user is through
+    const unsigned t = atomicAdd(a.ticket, 1u);
+    if (t == a.total_blocks - 1) *a.ticket = 0;   // last ticket of the launch: rearm the slot for its next call
+    s_ticket = t;
+    if (a.flow)
+    {
+      /* streaming: the previous call may still be writing the history this CTA reads -- for the deltas of
+       * the call's first 2m samples (its first chunk is the earliest) or for rolling a short call's history */
+      const unsigned jb0 = t / (a.channels * a.groups);
+      const unsigned first = jb0 * (blockDim.x >> 5);
+      const bool reads_hist = (first < a.sched.nchunks && chunk_span(a.sched, first).t0 < a.sched.period) ||
+                              (a.roll_hist && a.sched.n < a.sched.period);
+      if (reads_hist) wait_counter(a.prev_sync, a.prev_hist_target, a.error);
+    }
+  }
+  __syncthreads();
+  scan_emit_body<F, WINDOW, VEC, EMIT, MODE, GEO>(a, s_ticket, smem_raw, &s_done);
+}
+
+/* one call = TWO chain sets in one launch: a wide body over the full warp groups and a narrow tail over the
+ * remaining bins (sdft_launch.hpp explains when).  Bins are independent, so the two sets share nothing but the
+ * samples, the state buffers and the hand-over counters; what they must share is the MACHINE -- a tail launched on
+ * its own streams 512-byte row segments from a handful of warps per SM and takes as long as a tenth of the body.
+ * Every `every`-th ticket goes to the tail, the others to the body, both in their own order: a CTA still waits
+ * only for CTAs of its own set with smaller tickets, all of which have started.  Serial calls only. */
+template <typename F, int WINDOW, bool VEC, int EMIT, int MODE>
+__global__ void SDFT_B200_SCAN_BOUNDS scan_emit_mixed_kernel(const ChainArgs<F> body, const ChainArgs<F> tail, const unsigned every)
+{
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  __shared__ unsigned s_ticket;
+  __shared__ unsigned s_done;
+  grid_dependency_wait();
+  asm volatile("griddepcontrol.launch_dependents;");
+  if (threadIdx.x == 0)
+  {
+    s_done = 0;
+    const unsigned t = atomicAdd(body.ticket, 1u);
+    if (t == body.total_blocks + tail.total_blocks - 1) *body.ticket = 0;
+    s_ticket = t;
+  }
+  __syncthreads();
+  const unsigned t = s_ticket;
+  const unsigned slot = t / every;
+  if ((t + 1u) % every == 0u && slot < tail.total_blocks)
+    scan_emit_body<F, WINDOW, VEC, EMIT, MODE, GEO_NARROW>(tail, slot, smem_raw, &s_done);
+  else
+    scan_emit_body<F, WINDOW, VEC, EMIT, MODE, GEO_WIDE>(body, t - min(slot, tail.total_blocks), smem_raw, &s_done);
+}
 
 /* dynamic shared memory of one scan/emit CTA of `warps` warps and chunk length `chunk` */
 template <typename F, int GEO>

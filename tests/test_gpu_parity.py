@@ -247,8 +247,8 @@ def test_large_and_odd_dft_sizes(SDFT, m, fd):
 
 @pytest.mark.parametrize("m,window", [(2048, "hann"), (1024, "blackman"), (2000, "hamming")])
 def test_float_calls_split_into_wide_body_and_narrow_tail(SDFT, m, window, monkeypatch):
-    """Long float calls whose last wide warp group would be mostly empty run as two launches over disjoint bin
-    ranges (sdft_launch.hpp: ScanPart): rows, synthesized samples and state against the oracle over several calls,
+    """Long float calls whose last wide warp group would be mostly empty run as two chain sets over disjoint bin
+    ranges in one launch (sdft_launch.hpp: ScanPart, scan_emit_mixed_kernel): rows, synthesized samples and state against the oracle over several calls,
     with a state-only call and a region of interest in between, and against the same plan with the split
     disabled (identical up to the order in which the tail's carries are added)."""
     import torch
@@ -273,7 +273,8 @@ def test_float_calls_split_into_wide_body_and_narrow_tail(SDFT, m, window, monke
         assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
         y, yw = g.isdft(got).cpu().numpy(), o.isdft(want)
         assert np.abs(y.astype(np.float64) - yw).max() <= 2e-4 * max(np.abs(yw).max(), 1e-3)
-    assert g.launches - launches0 == 2 * 3 + 2, "every long call is two scan launches"
+    assert g.launches - launches0 == 3 + 2, "one scan launch per call (+ two synthesis launches)"
+    assert g._lib.sdft_b200_split_count(g._h) == 3 and one._lib.sdft_b200_split_count(one._h) == 0
     cg, hg, ag, pg = g.state()
     co, ho, ao, po = o.state()
     assert cg == co and np.array_equal(_bits(hg), _bits(ho)) and np.array_equal(_bits(pg), _bits(po))

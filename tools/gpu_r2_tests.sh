@@ -2,14 +2,11 @@
 TAG=${1:-t}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "row_pointer or single_sample" 2>&1 | tail -3
-timeout 600 python bench.py --steps 3 --no-cpu --no-sharded > $OUT/bench_quick.json 2> $OUT/bench_quick.err; echo "bench exit $?"
-python - <<PY
-import json
-d=json.load(open("$OUT/bench_quick.json"))
-print(d["value"], d["roofline"]["frac"])
-print(json.dumps(d["other_configs"]["row_pointer_variant"]))
-print(json.dumps(d["other_configs"]["single_sample_calls"]))
-print({k:v for k,v in d["e2e"].items() if k in ("bound","pcie_ceiling_GBps","frac_of_pcie")})
-PY
-tail -3 $OUT/bench_quick.err
+for NS in 0 1; do
+  export SDFT_B200_NO_SPLIT=$NS
+  python tools/quick_bench.py --n 4194304 --m 2048 --fd f32 --latency 0.5 --reps 5 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('no_split=$NS m=2048', round(d['GBps']))"
+  python tools/quick_bench.py --n 2097152 --m 1024 --fd f32 --reps 5 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('no_split=$NS m=1024', round(d['GBps']))"
+done
+unset SDFT_B200_NO_SPLIT
+timeout 1500 python -m pytest tests -m gpu -x -q --durations=5 > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log
+tail -8 $OUT/pytest_gpu.log
