@@ -276,7 +276,9 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
   for (int q = 0; q < nparts; ++q)
   {
     ScanPart& sp = parts[q];
-    const unsigned chunk = choose_chunk(p, n, sp.geo);
+    /* both chain sets of a split call cut time the same way: the tail's CTAs then carry as many steps as the
+     * body's and pay the per-CTA latencies (ticket, deltas, look-back) as rarely */
+    const unsigned chunk = (q == 0) ? choose_chunk(p, n, sp.geo) : args[0].sched.chunk;
     const Schedule sched = make_schedule(p->cursor, n, m, chunk);
     const size_t wc = (sp.geo == GEO_NARROW) ? (size_t)Geo<F, GEO_NARROW>::WC : (size_t)Geo<F, GEO_WIDE>::WC;
     /* both chain sets of a split call run in one launch: one CTA width */
