@@ -85,4 +85,28 @@ SDFT_B200_HD inline ChunkSpan chunk_span(const Schedule& s, unsigned j)
   return c;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * ticket interleaving of a mixed launch (scan_emit_mixed_kernel): `body` + `tail` work tickets are handed out
+ * by ONE counter; every `every`-th ticket (indices every-1, 2*every-1, ...) belongs to the tail set until the tail
+ * has `tail` of them, all others to the body set.  Both sets see their own tickets in increasing order, so a CTA
+ * only ever waits for CTAs with smaller global tickets.  every = (body + tail) / tail keeps the last tail
+ * ticket inside the launch.
+ * ---------------------------------------------------------------------------------------------- */
+struct MixedTicket
+{
+  bool is_tail;
+  unsigned local;     // ticket inside its own set
+};
+
+SDFT_B200_HD inline unsigned mixed_every(unsigned body, unsigned tail) { return (body + tail) / tail; }
+
+SDFT_B200_HD inline MixedTicket mixed_ticket(unsigned t, unsigned every, unsigned tail)
+{
+  const unsigned slot = t / every;               // tail tickets handed out before t (if the tail still had some)
+  MixedTicket r;
+  r.is_tail = ((t + 1u) % every == 0u) && (slot < tail);
+  r.local = r.is_tail ? slot : t - (slot < tail ? slot : tail);
+  return r;
+}
+
 }  // namespace sdftb200

@@ -385,7 +385,7 @@ bool analysis_chained(Plan* p, size_t n, const T* x, size_t x_stride, cx<F>* out
     }
     const unsigned total = args[0].total_blocks + args[1].total_blocks;
     args[0].finish_blocks = args[1].finish_blocks = total;
-    const unsigned every = total / args[1].total_blocks;          // every `every`-th ticket is a tail ticket
+    const unsigned every = mixed_every(args[0].total_blocks, args[1].total_blocks);   // every `every`-th ticket is a tail ticket
     p->split_calls++;
     if (out) launch_mixed<F, EMIT_ROWS>(p, args[0], args[1], every, can_vectorize<F>(p, out, out_stride), parts[0].warps);
     else launch_mixed<F, EMIT_NONE>(p, args[0], args[1], every, false, parts[0].warps);

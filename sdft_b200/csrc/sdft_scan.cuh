@@ -921,12 +921,9 @@ __global__ void SDFT_B200_SCAN_BOUNDS scan_emit_mixed_kernel(const ChainArgs<F> 
     s_ticket = t;
   }
   __syncthreads();
-  const unsigned t = s_ticket;
-  const unsigned slot = t / every;
-  if ((t + 1u) % every == 0u && slot < tail.total_blocks)
-    scan_emit_body<F, WINDOW, VEC, EMIT, MODE, GEO_NARROW>(tail, slot, smem_raw, &s_done);
-  else
-    scan_emit_body<F, WINDOW, VEC, EMIT, MODE, GEO_WIDE>(body, t - min(slot, tail.total_blocks), smem_raw, &s_done);
+  const MixedTicket mt = mixed_ticket(s_ticket, every, tail.total_blocks);     // sdft_chunks.hpp
+  if (mt.is_tail) scan_emit_body<F, WINDOW, VEC, EMIT, MODE, GEO_NARROW>(tail, mt.local, smem_raw, &s_done);
+  else scan_emit_body<F, WINDOW, VEC, EMIT, MODE, GEO_WIDE>(body, mt.local, smem_raw, &s_done);
 }
 
 /* dynamic shared memory of one scan/emit CTA of `warps` warps and chunk length `chunk` */

@@ -52,6 +52,32 @@ int main()
     }
     ++cases;
   }
-  printf("%ld schedules ok\n", cases);
+  // ticket interleaving of a mixed launch: a bijection onto (body tickets, tail tickets), each set in increasing order
+  long mixes = 0;
+  for (int it = 0; it < 3000; ++it)
+  {
+    const unsigned tail = 1 + (unsigned)(rnd() % 200), body = (unsigned)(rnd() % 4000) + (it % 7 == 0 ? 0 : tail);
+    const unsigned every = mixed_every(body, tail);
+    unsigned next_body = 0, next_tail = 0;
+    for (unsigned t = 0; t < body + tail; ++t)
+    {
+      const MixedTicket mt = mixed_ticket(t, every, tail);
+      unsigned& expect = mt.is_tail ? next_tail : next_body;
+      if (every == 0 || mt.local != expect || (mt.is_tail ? mt.local >= tail : mt.local >= body))
+      {
+        printf("mixed ticket violation: body=%u tail=%u every=%u t=%u -> %s %u (expected %u)\n", body, tail, every, t,
+               mt.is_tail ? "tail" : "body", mt.local, expect);
+        return 1;
+      }
+      ++expect;
+    }
+    if (next_body != body || next_tail != tail)
+    {
+      printf("mixed tickets do not cover both sets: body=%u/%u tail=%u/%u every=%u\n", next_body, body, next_tail, tail, every);
+      return 1;
+    }
+    ++mixes;
+  }
+  printf("%ld schedules ok, %ld ticket interleavings ok\n", cases, mixes);
   return 0;
 }
